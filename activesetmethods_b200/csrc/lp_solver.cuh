@@ -1,0 +1,889 @@
+// Restarted, reflected Halpern PDHG for   min c'x  s.t.  rl <= Kx <= ru,  lb <= x <= ub   on sm_100a.
+//
+// This is the component that stands where GLPK's simplex stands in the reference
+// (MOI.optimize!(qp.model), /root/reference/src/algorithms/subproblem.jl:490).  Algorithm (literature,
+// SURVEY.md App. F): Ruiz + Pock-Chambolle diagonal preconditioning, bound/objective rescaling, PDHG with
+// reflection and Halpern anchoring, fixed-point-error restarts (sufficient / necessary / artificial),
+// PID-controlled primal weight, KKT termination in the unscaled space, Farkas-ray infeasibility test.
+//
+// Kernels (all hand-written; B = batch, vectors element-major v[i*B+s]):
+//   k_primal<CHECK>   CSC pass  A'y fused with the primal box projection, reflection and Halpern step
+//   k_dual<CHECK>     CSR pass  A xbar fused with the dual prox and Halpern step
+//   k_dual_resid      CSC pass  A'y+ for reduced costs / dual residual / dual objective   (check only)
+//   k_ray_rows/cols   Farkas certificate pieces                                          (check only)
+//   k_decide          one block per LP: deterministic second-stage reductions, termination, restart, PID
+//   k_apply           restart or Halpern update after a check
+//   k_ruiz_* / k_build_scaled / k_prepare_* / k_finalize   preconditioning and (un)scaling
+// A solve launches a CUDA graph of `check_every` iterations per host round trip; the only host<->device
+// traffic inside the loop is the 4-byte active counter.
+#pragma once
+#include "util.cuh"
+
+namespace asmb {
+
+struct ScenState {
+    double omega, eta, sb, sc;
+    double nq_un, nc_un;
+    double r0, r_prev, e_sum, e_prev;
+    double pobj, dobj, pres, dres, gap;
+    long long total;
+    int k0;
+    int restarts;
+    int status;        // -1 while running, else ASM_LP_*
+    int restart_flag;  // set by k_decide, consumed by k_apply
+};
+
+struct DevParams {
+    double eps_rel, eps_infeas;
+    double b_suf, b_nec, b_art;
+    double kp, ki, kd;
+    int verbose;
+};
+
+// reduction slots
+enum {
+    Q_DX2 = 0,   // sum (xp - x)^2
+    Q_DXA2,      // sum (xp - xa)^2
+    Q_POBJ,      // sum cs * xp
+    Q_DY2,       // sum (yp - y)^2
+    Q_DYADX,     // sum dy * A dx
+    Q_DYA2,      // sum (yp - ya)^2
+    Q_PRES2,     // unscaled primal residual^2
+    Q_DOBJ_ROW,  // row part of the dual objective (scaled units)
+    Q_DRES2,     // unscaled dual residual^2
+    Q_DOBJ_COL,  // column part of the dual objective (scaled units)
+    Q_RAY_ROW,   // Farkas: sum rl*ray+ + ru*ray-   (scaled units)
+    Q_RAY_MAX,   // max |ray * dr|
+    Q_RAY_COL,   // Farkas: box support of -(A'ray)
+    Q_KTY_MAX,   // max |(A'ray)_j / dc_j|
+    Q_COUNT
+};
+// preparation slots (reuse the same partial buffer)
+enum { P_C2 = 0, P_CUN2, P_Q2, P_QUN2, P_COUNT };
+
+struct LpView {
+    int n, m, B;
+    int nbx_rows, nbx_cols;
+    const int *row_ptr, *col_idx, *col_ptr, *row_idx, *csc_src;
+    // unscaled data
+    const double *vals, *c, *lb, *ub, *rl, *ru;
+    // scaled data
+    double *A, *AT, *dr, *dc, *sr, *scf, *cs, *lbs, *ubs, *rls, *rus;
+    // iterates
+    double *x, *xa, *xp, *xbar, *gy, *gyp;
+    double *y, *ya, *yp, *ray;
+    // results (unscaled)
+    double *xo, *yo, *dlo, *dup;
+    double *partials;
+    ScenState *state;
+    const DevParams *prm;
+    int *n_active;
+};
+
+// =================================== preconditioning ======================================================
+template <bool BATCH, bool SUM>
+__global__ void __launch_bounds__(kThreads) k_ruiz_rows(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const double dri = v.dr[i * B + mp.s];
+        double a = 0.0;
+        for (int k = v.row_ptr[i]; k < v.row_ptr[i + 1]; ++k) {
+            double t = fabs(v.vals[(int64_t)k * B + mp.s] * dri * v.dc[(int64_t)v.col_idx[k] * B + mp.s]);
+            a = SUM ? a + t : fmax(a, t);
+        }
+        v.sr[i * B + mp.s] = a > 0.0 ? 1.0 / sqrt(a) : 1.0;
+    }
+}
+template <bool BATCH, bool SUM>
+__global__ void __launch_bounds__(kThreads) k_ruiz_cols(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const double dcj = v.dc[j * B + mp.s];
+        double a = 0.0;
+        for (int k = v.col_ptr[j]; k < v.col_ptr[j + 1]; ++k) {
+            double t = fabs(v.vals[(int64_t)v.csc_src[k] * B + mp.s] * v.dr[(int64_t)v.row_idx[k] * B + mp.s] * dcj);
+            a = SUM ? a + t : fmax(a, t);
+        }
+        v.scf[j * B + mp.s] = a > 0.0 ? 1.0 / sqrt(a) : 1.0;
+    }
+}
+__global__ void k_mul_inplace(double *__restrict__ a, const double *__restrict__ b, int64_t n) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        a[t] *= b[t];
+}
+__global__ void k_fill(double *__restrict__ a, double val, int64_t n) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        a[t] = val;
+}
+// scaled matrix in both orders; the product is formed identically so A and AT hold the same doubles
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_build_scaled_csr(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const double dri = v.dr[i * B + mp.s];
+        for (int k = v.row_ptr[i]; k < v.row_ptr[i + 1]; ++k)
+            v.A[(int64_t)k * B + mp.s] = v.vals[(int64_t)k * B + mp.s] * dri * v.dc[(int64_t)v.col_idx[k] * B + mp.s];
+    }
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_build_scaled_csc(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const double dcj = v.dc[j * B + mp.s];
+        for (int k = v.col_ptr[j]; k < v.col_ptr[j + 1]; ++k)
+            v.AT[(int64_t)k * B + mp.s] =
+                v.vals[(int64_t)v.csc_src[k] * B + mp.s] * v.dr[(int64_t)v.row_idx[k] * B + mp.s] * dcj;
+    }
+}
+
+// first pass over the vectors: diagonal scaling + the norms that define sb, sc, omega0 and the
+// termination denominators
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_prepare_cols(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        const double d = v.dc[e], cj = v.c[e];
+        const double c0 = cj * d;
+        v.cs[e] = c0;
+        v.lbs[e] = v.lb[e] / d;
+        v.ubs[e] = v.ub[e] / d;
+        acc[0] += c0 * c0;
+        acc[1] += cj * cj;
+    }
+    block_reduce_store<BATCH, 2>(acc, 0u, v.partials, P_C2, B);
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_prepare_rows(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    double q2 = 0.0, qun2 = 0.0;
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        const double d = v.dr[e], l = v.rl[e], u = v.ru[e];
+        const double ls = l * d, us = u * d;
+        v.rls[e] = ls;
+        v.rus[e] = us;
+        if (isfinite(l)) {
+            q2 += ls * ls;
+            qun2 += l * l;
+        }
+        if (isfinite(u) && u != l) {
+            q2 += us * us;
+            qun2 += u * u;
+        }
+    }
+    double acc[2] = {q2, qun2};
+    block_reduce_store<BATCH, 2>(acc, 0u, v.partials, P_Q2, B);
+}
+// one block per scenario: scalars of the scaled problem
+__global__ void __launch_bounds__(kFinalThreads) k_init_state(LpView v) {
+    const int s = blockIdx.x, B = v.B;
+    double c2 = final_reduce(v.partials, P_C2, v.nbx_cols, B, s, false);
+    double cun2 = final_reduce(v.partials, P_CUN2, v.nbx_cols, B, s, false);
+    double q2 = final_reduce(v.partials, P_Q2, v.nbx_rows, B, s, false);
+    double qun2 = final_reduce(v.partials, P_QUN2, v.nbx_rows, B, s, false);
+    if (threadIdx.x == 0) {
+        ScenState st;
+        st.sb = 1.0 / (sqrt(q2) + 1.0);
+        st.sc = 1.0 / (sqrt(c2) + 1.0);
+        const double nc = sqrt(c2) * st.sc, nq = sqrt(q2) * st.sb;
+        st.omega = (nc > 0.0 && nq > 0.0) ? nc / nq : 1.0;
+        st.eta = 0.998;  // ||A||_2 <= 1 after Pock-Chambolle (alpha = 1) scaling
+        st.nq_un = sqrt(qun2);
+        st.nc_un = sqrt(cun2);
+        st.r0 = 0.0;
+        st.r_prev = INFINITY;
+        st.e_sum = 0.0;
+        st.e_prev = 0.0;
+        st.pobj = st.dobj = 0.0;
+        st.pres = st.dres = st.gap = INFINITY;
+        st.total = 0;
+        st.k0 = 0;
+        st.restarts = 0;
+        st.status = -1;
+        st.restart_flag = 0;
+        v.state[s] = st;
+    }
+}
+// second pass: bound/objective rescaling and the starting point (x0, y0 are unscaled warm starts or 0)
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_prepare_finish(LpView v, int warm) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const double sb = v.state[mp.s].sb, sc = v.state[mp.s].sc;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        v.cs[e] *= sc;
+        const double l = v.lbs[e] * sb, u = v.ubs[e] * sb;
+        v.lbs[e] = l;
+        v.ubs[e] = u;
+        double x0 = warm ? v.xo[e] / v.dc[e] * sb : 0.0;
+        x0 = fmin(fmax(x0, l), u);
+        v.x[e] = x0;
+        v.xa[e] = x0;
+    }
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        v.rls[e] *= sb;
+        v.rus[e] *= sb;
+        double y0 = warm ? v.yo[e] / v.dr[e] * sc : 0.0;
+        if (!isfinite(v.rl[e])) y0 = fmin(y0, 0.0);
+        if (!isfinite(v.ru[e])) y0 = fmax(y0, 0.0);
+        v.y[e] = y0;
+        v.ya[e] = y0;
+    }
+}
+
+// =================================== PDHG iteration ========================================================
+// Primal half: g = cs - A'y ; xp = proj_box(x - tau g) ; xbar = 2 xp - x ; Halpern x <- w xbar + (1-w) xa.
+// CHECK: keep xp, g and xbar, leave x untouched (k_apply finishes the step after the restart decision).
+template <bool BATCH, bool CHECK>
+__global__ void __launch_bounds__(kThreads) k_primal(LpView v, int jit) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const ScenState *st = v.state + mp.s;
+    const bool live = st->status < 0;
+    const double tau = live ? st->eta / st->omega : 0.0;
+    const int kk = st->k0 + jit + 1;
+    const double w = (double)kk / ((double)kk + 1.0);
+    double acc[3] = {0.0, 0.0, 0.0};
+    if (live) {
+        for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+            const int64_t e = j * B + mp.s;
+            double a = 0.0;
+            const int k1 = v.col_ptr[j + 1];
+            for (int k = v.col_ptr[j]; k < k1; ++k)
+                a += v.AT[(int64_t)k * B + mp.s] * v.y[(int64_t)v.row_idx[k] * B + mp.s];
+            const double cj = v.cs[e];
+            const double g = cj - a;
+            const double xv = v.x[e];
+            const double xpv = fmin(fmax(xv - tau * g, v.lbs[e]), v.ubs[e]);
+            const double xb = 2.0 * xpv - xv;
+            v.xbar[e] = xb;
+            if (CHECK) {
+                v.xp[e] = xpv;
+                v.gy[e] = g;
+                const double dx = xpv - xv, da = xpv - v.xa[e];
+                acc[0] += dx * dx;
+                acc[1] += da * da;
+                acc[2] += cj * xpv;
+            } else {
+                v.x[e] = w * xb + (1.0 - w) * v.xa[e];
+            }
+        }
+    }
+    if (CHECK) block_reduce_store<BATCH, 3>(acc, 0u, v.partials, Q_DX2, B);
+}
+
+// Dual half: t = A xbar - y/sigma ; yp = sigma (proj_[rl,ru](t) - t) ; Halpern y <- w (2 yp - y) + (1-w) ya.
+template <bool BATCH, bool CHECK>
+__global__ void __launch_bounds__(kThreads) k_dual(LpView v, int jit) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const ScenState *st = v.state + mp.s;
+    const bool live = st->status < 0;
+    const double sigma = live ? st->eta * st->omega : 1.0;
+    const double isig = 1.0 / sigma;
+    const int kk = st->k0 + jit + 1;
+    const double w = (double)kk / ((double)kk + 1.0);
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (live) {
+        const double inv_sb = 1.0 / st->sb;
+        for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+            const int64_t e = i * B + mp.s;
+            double a = 0.0, ax = 0.0;
+            const int k1 = v.row_ptr[i + 1];
+            for (int k = v.row_ptr[i]; k < k1; ++k) {
+                const double av = v.A[(int64_t)k * B + mp.s];
+                const int64_t ce = (int64_t)v.col_idx[k] * B + mp.s;
+                a += av * v.xbar[ce];
+                if (CHECK) ax += av * v.x[ce];
+            }
+            const double yv = v.y[e];
+            const double t = a - yv * isig;
+            const double l = v.rls[e], u = v.rus[e];
+            const double ypv = t < l ? sigma * (l - t) : (t > u ? sigma * (u - t) : 0.0);
+            if (CHECK) {
+                v.yp[e] = ypv;
+                const double dy = ypv - yv, da = ypv - v.ya[e];
+                const double adx = 0.5 * (a - ax);  // A (xp - x)
+                const double axp = 0.5 * (a + ax);  // A xp
+                acc[0] += dy * dy;
+                acc[1] += dy * adx;
+                acc[2] += da * da;
+                const double viol = (axp < l ? l - axp : (axp > u ? axp - u : 0.0)) * inv_sb / v.dr[e];
+                acc[3] += viol * viol;
+                // dual objective: rl y+ + ru y- (scaled units; unused side may be infinite -> guard)
+                acc[4] += ypv > 0.0 ? l * ypv : (ypv < 0.0 ? u * ypv : 0.0);
+            } else {
+                v.y[e] = w * (2.0 * ypv - yv) + (1.0 - w) * v.ya[e];
+            }
+        }
+    }
+    if (CHECK) block_reduce_store<BATCH, 5>(acc, 0u, v.partials, Q_DY2, B);
+}
+
+// Reduced costs of (xp, yp):  rc = cs - A'yp ; dual residual and column part of the dual objective.
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_dual_resid(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const ScenState *st = v.state + mp.s;
+    const bool live = st->status < 0;
+    double acc[2] = {0.0, 0.0};
+    if (live) {
+        const double inv_sc = 1.0 / st->sc;
+        for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+            const int64_t e = j * B + mp.s;
+            double a = 0.0;
+            const int k1 = v.col_ptr[j + 1];
+            for (int k = v.col_ptr[j]; k < k1; ++k)
+                a += v.AT[(int64_t)k * B + mp.s] * v.yp[(int64_t)v.row_idx[k] * B + mp.s];
+            const double rc = v.cs[e] - a;
+            v.gyp[e] = rc;
+            const double xpv = v.xp[e], l = v.lbs[e], u = v.ubs[e];
+            // reduced costs count as multipliers only where the iterate sits on a finite bound
+            const double rpos = (isfinite(l) && xpv <= l) ? fmax(rc, 0.0) : 0.0;
+            const double rneg = (isfinite(u) && xpv >= u) ? fmin(rc, 0.0) : 0.0;
+            const double res = (rc - rpos - rneg) * inv_sc / v.dc[e];
+            acc[0] += res * res;
+            acc[1] += (rpos > 0.0 ? l * rpos : 0.0) + (rneg < 0.0 ? u * rneg : 0.0);
+        }
+    }
+    block_reduce_store<BATCH, 2>(acc, 0u, v.partials, Q_DRES2, B);
+}
+
+// Farkas ray from the iterate difference dy = yp - y, projected on the sign cone of the infinite sides.
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ray_rows(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const bool live = v.state[mp.s].status < 0;
+    double acc[2] = {0.0, 0.0};
+    if (live) {
+        for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+            const int64_t e = i * B + mp.s;
+            double d = v.yp[e] - v.y[e];
+            const double l = v.rls[e], u = v.rus[e];
+            if (!isfinite(l)) d = fmin(d, 0.0);
+            if (!isfinite(u)) d = fmax(d, 0.0);
+            v.ray[e] = d;
+            acc[0] += d > 0.0 ? l * d : (d < 0.0 ? u * d : 0.0);
+            acc[1] = fmax(acc[1], fabs(d * v.dr[e]));
+        }
+    }
+    block_reduce_store<BATCH, 2>(acc, 2u, v.partials, Q_RAY_ROW, B);
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ray_cols(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const bool live = v.state[mp.s].status < 0;
+    double acc[2] = {0.0, 0.0};
+    if (live) {
+        for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+            const int64_t e = j * B + mp.s;
+            double a = 0.0;
+            const int k1 = v.col_ptr[j + 1];
+            for (int k = v.col_ptr[j]; k < k1; ++k)
+                a += v.AT[(int64_t)k * B + mp.s] * v.ray[(int64_t)v.row_idx[k] * B + mp.s];
+            // support of the box in direction -(A'ray): min over [lb, ub] of -(a) x
+            const double t = -a;
+            acc[0] += t > 0.0 ? t * v.lbs[e] : (t < 0.0 ? t * v.ubs[e] : 0.0);
+            acc[1] = fmax(acc[1], fabs(a / v.dc[e]));
+        }
+    }
+    block_reduce_store<BATCH, 2>(acc, 2u, v.partials, Q_RAY_COL, B);
+}
+
+// One block per LP: finish the reductions and take every scalar decision of the check.
+__global__ void __launch_bounds__(kFinalThreads) k_decide(LpView v, int jit, int steps_in_graph) {
+    const int s = blockIdx.x, B = v.B;
+    ScenState *sp = v.state + s;
+    if (sp->status >= 0) return;  // uniform per block
+    double q[Q_COUNT];
+    for (int i = 0; i < Q_COUNT; ++i) {
+        const bool rows = (i >= Q_DY2 && i <= Q_DOBJ_ROW) || i == Q_RAY_ROW || i == Q_RAY_MAX;
+        const bool is_max = (i == Q_RAY_MAX || i == Q_KTY_MAX);
+        q[i] = final_reduce(v.partials, i, rows ? v.nbx_rows : v.nbx_cols, B, s, is_max);
+    }
+    if (threadIdx.x != 0) return;
+    ScenState st = *sp;
+    const DevParams P = *v.prm;
+    const double tau = st.eta / st.omega, sigma = st.eta * st.omega;
+    const int k = st.k0 + jit + 1;
+    const long long total = st.total + jit + 1;
+    double r2 = q[Q_DX2] / tau - 2.0 * q[Q_DYADX] + q[Q_DY2] / sigma;
+    const double r = sqrt(fmax(r2, 0.0));
+    const double unit = 1.0 / (st.sb * st.sc);
+    const double pobj = q[Q_POBJ] * unit;
+    const double dobj = (q[Q_DOBJ_ROW] + q[Q_DOBJ_COL]) * unit;
+    const double pres = sqrt(q[Q_PRES2]), dres = sqrt(q[Q_DRES2]);
+    const double gap = fabs(pobj - dobj);
+    st.pobj = pobj;
+    st.dobj = dobj;
+    st.pres = pres;
+    st.dres = dres;
+    st.gap = gap;
+    int status = -1;
+    if (pres <= P.eps_rel * (1.0 + st.nq_un) && dres <= P.eps_rel * (1.0 + st.nc_un) &&
+        gap <= P.eps_rel * (1.0 + fabs(pobj) + fabs(dobj)))
+        status = ASM_LP_OPTIMAL;
+    if (status < 0) {
+        // Farkas certificate: ray'rl+ + ray'ru- - max_box (K'ray)'x > 0  (all terms carry 1/(sb sc);
+        // normalise by ||ray||_inf in unscaled units = Q_RAY_MAX / sc)
+        const double nr = q[Q_RAY_MAX] / st.sc;
+        if (nr > 0.0) {
+            const double robj = (q[Q_RAY_ROW] + q[Q_RAY_COL]) * unit / nr;
+            const double kty = q[Q_KTY_MAX] / st.sc / nr;
+            if (robj > P.eps_infeas * fmax(1.0, kty)) status = ASM_LP_INFEASIBLE;
+        }
+    }
+    if (!(r == r) || !(pobj == pobj)) status = ASM_LP_NUMERICAL_ERROR;
+    int restart = 0;
+    if (status < 0) {
+        if (k == 1) {
+            st.r0 = r;
+        } else if (jit + 1 == steps_in_graph) {
+            if (r <= P.b_suf * st.r0)
+                restart = 1;
+            else if (r <= P.b_nec * st.r0 && r > st.r_prev)
+                restart = 1;
+            else if ((double)k >= P.b_art * (double)total)
+                restart = 1;
+        }
+        st.r_prev = r;
+        if (restart) {
+            const double ddx = sqrt(q[Q_DXA2]), ddy = sqrt(q[Q_DYA2]);
+            if (ddx > 1e-300 && ddy > 1e-300) {
+                const double e = log(st.omega * ddx / ddy);
+                st.e_sum += e;
+                const double dlog = -(P.kp * e + P.ki * st.e_sum + P.kd * (e - st.e_prev));
+                st.omega = exp(log(st.omega) + dlog);
+                st.e_prev = e;
+            }
+            st.restarts += 1;
+            st.r_prev = INFINITY;
+        }
+    }
+    if (P.verbose && s == 0)
+        printf("[pdhg] it %lld k %d pres %.3e dres %.3e gap %.3e pobj %.10e r %.3e w %.3e restarts %d%s\n", total, k,
+               pres, dres, gap, pobj, r, st.omega, st.restarts, restart ? " R" : "");
+    st.restart_flag = restart;
+    if (jit + 1 == steps_in_graph) {
+        st.total += steps_in_graph;
+        st.k0 = restart ? 0 : st.k0 + steps_in_graph;
+    }
+    if (status >= 0) {
+        st.total = total;
+        st.status = status;
+        st.restart_flag = 2;  // k_apply: freeze at (xp, yp)
+        atomicSub(v.n_active, 1);
+    }
+    *sp = st;
+}
+
+// After a check: restart or freeze (x = xa = xp, y = ya = yp), else complete the Halpern step with the w of
+// that step (kstep[s] = k of the step, stored before k_decide advanced k0).
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_apply(LpView v, const int *__restrict__ kstep) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const ScenState *st = v.state + mp.s;
+    const int flag = st->restart_flag;
+    if (st->status >= 0 && flag != 2) return;
+    const int kk = kstep[mp.s];
+    const double w = (double)kk / ((double)kk + 1.0);
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        if (flag) {
+            const double t = v.xp[e];
+            v.x[e] = t;
+            v.xa[e] = t;
+        } else {
+            v.x[e] = w * v.xbar[e] + (1.0 - w) * v.xa[e];
+        }
+    }
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        if (flag) {
+            const double t = v.yp[e];
+            v.y[e] = t;
+            v.ya[e] = t;
+        } else {
+            v.y[e] = w * (2.0 * v.yp[e] - v.y[e]) + (1.0 - w) * v.ya[e];
+        }
+    }
+}
+// scenarios that finished at this check are frozen exactly once
+__global__ void k_after_apply(ScenState *st, int B) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < B && st[s].status >= 0 && st[s].restart_flag == 2) st[s].restart_flag = 3;
+}
+__global__ void k_store_kstep(const ScenState *st, int *kstep, int jit, int B) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < B) kstep[s] = st[s].k0 + jit + 1;
+}
+__global__ void k_mark_padding(ScenState *st, int Buser, int B) {
+    int s = Buser + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < B) st[s].status = ASM_LP_OPTIMAL;
+}
+
+// unscale the final iterate; bound duals from the reduced costs of the last check
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_finalize(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const ScenState *st = v.state + mp.s;
+    const double inv_sb = 1.0 / st->sb, inv_sc = 1.0 / st->sc;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        const double xs = v.xp[e], l = v.lbs[e], u = v.ubs[e];
+        const bool at_l = isfinite(l) && xs <= l, at_u = isfinite(u) && xs >= u;
+        // on a bound return the caller's bound itself so that exact comparisons (subproblem.jl:522-529) hold
+        v.xo[e] = at_l ? v.lb[e] : (at_u ? v.ub[e] : xs * v.dc[e] * inv_sb);
+        const double rc = v.gyp[e] * inv_sc / v.dc[e];
+        v.dlo[e] = at_l ? fmax(rc, 0.0) : 0.0;
+        v.dup[e] = at_u ? fmin(rc, 0.0) : 0.0;
+    }
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        v.yo[e] = v.yp[e] * v.dr[e] * inv_sc;
+    }
+}
+
+// ================================================================================================================
+#define ASM_KL(...)      \
+    do {                 \
+        __VA_ARGS__;     \
+        ++launches;      \
+    } while (0)
+// launch the <BATCH> instantiation that matches this handle
+#define ASM_KB(kern, geo, ...)                                                    \
+    do {                                                                          \
+        if (B > 1)                                                                \
+            kern<true><<<(geo).grid, (geo).block, 0, stream>>>(__VA_ARGS__);      \
+        else                                                                      \
+            kern<false><<<(geo).grid, (geo).block, 0, stream>>>(__VA_ARGS__);     \
+        ++launches;                                                               \
+    } while (0)
+#define ASM_KB2(kern, flag, geo, ...)                                                   \
+    do {                                                                                \
+        if (B > 1)                                                                      \
+            kern<true, flag><<<(geo).grid, (geo).block, 0, stream>>>(__VA_ARGS__);      \
+        else                                                                            \
+            kern<false, flag><<<(geo).grid, (geo).block, 0, stream>>>(__VA_ARGS__);     \
+        ++launches;                                                                     \
+    } while (0)
+
+class LpSolver {
+   public:
+    int n = 0, m = 0, B = 1, Buser = 1;
+    int64_t nnz = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // pattern
+    DBuf<int> row_ptr, col_idx, col_ptr, row_idx, csc_src;
+    std::vector<int> h_row_ptr, h_col_idx;
+    // data (unscaled, element-major)
+    DBuf<double> vals, c, lb, ub, rl, ru, c0;
+    DBuf<double> A, AT, dr, dc, sr, scf, cs, lbs, ubs, rls, rus;
+    DBuf<double> x, xa, xp, xbar, gy, gyp, y, ya, yp, ray;
+    DBuf<double> xo, yo, dlo, dup, partials;
+    DBuf<ScenState> state;
+    DBuf<DevParams> prm;
+    DBuf<int> n_active, kstep;
+    Pinned pin_flag;
+    std::vector<ScenState> host_state;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_steps = 0;
+    int64_t launches_per_graph = 0;
+    bool has_solution = false;
+    int64_t launches = 0;
+    double last_loop_ms = 0.0;
+    int64_t last_iters = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    ~LpSolver() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+
+    // pattern: 0-based CSR with int64 row_ptr on the host
+    int init(int n_, int m_, int64_t nnz_, const int64_t *rp64, const int32_t *h_ci, int batch, cudaStream_t st) {
+        n = n_;
+        m = m_;
+        nnz = nnz_;
+        Buser = batch;
+        B = pad_batch(batch);
+        if (n <= 0 || m < 0 || nnz < 0 || batch < 1) return fail(ASM_E_INVALID, "bad LP dimensions");
+        if (nnz > 0x7fffffffLL) return fail(ASM_E_INVALID, "nnz exceeds 2^31-1");
+        if (rp64[0] != 0 || rp64[m] != nnz) return fail(ASM_E_INVALID, "row_ptr does not match nnz");
+        if (st) {
+            stream = st;
+        } else {
+            ASM_CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            own_stream = true;
+        }
+        ASM_CK(cudaEventCreate(&ev0));
+        ASM_CK(cudaEventCreate(&ev1));
+        // host CSC + map CSC position -> CSR position
+        h_row_ptr.resize(m + 1);
+        h_col_idx.resize(nnz);
+        std::vector<int> cp(n + 1, 0), ri(nnz), src(nnz);
+        for (int i = 0; i <= m; ++i) {
+            h_row_ptr[i] = (int)rp64[i];
+            if (i && rp64[i] < rp64[i - 1]) return fail(ASM_E_INVALID, "row_ptr not monotone");
+        }
+        for (int64_t k = 0; k < nnz; ++k) {
+            if (h_ci[k] < 0 || h_ci[k] >= n) return fail(ASM_E_INVALID, "column index out of range");
+            h_col_idx[k] = h_ci[k];
+            cp[h_ci[k] + 1]++;
+        }
+        for (int j = 0; j < n; ++j) cp[j + 1] += cp[j];
+        {
+            std::vector<int> cur(cp.begin(), cp.end() - 1);
+            for (int i = 0; i < m; ++i)
+                for (int k = h_row_ptr[i]; k < h_row_ptr[i + 1]; ++k) {
+                    int pos = cur[h_col_idx[k]]++;
+                    ri[pos] = i;
+                    src[pos] = k;
+                }
+        }
+        ASM_TRY(row_ptr.alloc(m + 1));
+        ASM_TRY(col_idx.alloc(nnz));
+        ASM_TRY(col_ptr.alloc(n + 1));
+        ASM_TRY(row_idx.alloc(nnz));
+        ASM_TRY(csc_src.alloc(nnz));
+        ASM_CK(cudaMemcpy(row_ptr.p, h_row_ptr.data(), (m + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        if (nnz) {
+            ASM_CK(cudaMemcpy(col_idx.p, h_col_idx.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+            ASM_CK(cudaMemcpy(row_idx.p, ri.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+            ASM_CK(cudaMemcpy(csc_src.p, src.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        ASM_CK(cudaMemcpy(col_ptr.p, cp.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        const size_t nB = (size_t)n * B, mB = (size_t)m * B, zB = (size_t)nnz * B;
+        DBuf<double> *colv[] = {&c, &lb, &ub, &dc, &scf, &cs, &lbs, &ubs, &x, &xa, &xp, &xbar, &gy, &gyp, &xo, &dlo, &dup};
+        for (auto *b : colv) ASM_TRY(b->alloc(nB));
+        DBuf<double> *rowv[] = {&rl, &ru, &dr, &sr, &rls, &rus, &y, &ya, &yp, &ray, &yo};
+        for (auto *b : rowv) ASM_TRY(b->alloc(mB));
+        ASM_TRY(vals.alloc(zB));
+        ASM_TRY(A.alloc(zB));
+        ASM_TRY(AT.alloc(zB));
+        ASM_TRY(c0.alloc(B));
+        ASM_TRY(partials.alloc((size_t)Q_COUNT * kMaxBlocksX * B));
+        ASM_TRY(state.alloc(B));
+        ASM_TRY(prm.alloc(1));
+        ASM_TRY(n_active.alloc(1));
+        ASM_TRY(kstep.alloc(B));
+        ASM_TRY(pin_flag.reserve(64));
+        host_state.resize(B);
+        ASM_TRY(c0.zero(stream));
+        ASM_TRY(xo.zero(stream));
+        ASM_TRY(yo.zero(stream));
+        ASM_TRY(vals.zero(stream));
+        ASM_TRY(partials.zero(stream));
+        ASM_CK(cudaStreamSynchronize(stream));
+        return ASM_OK;
+    }
+
+    LpView view() {
+        LpView v;
+        v.n = n;
+        v.m = m;
+        v.B = B;
+        v.nbx_rows = geo_for(m, B).grid.x;
+        v.nbx_cols = geo_for(n, B).grid.x;
+        v.row_ptr = row_ptr.p;
+        v.col_idx = col_idx.p;
+        v.col_ptr = col_ptr.p;
+        v.row_idx = row_idx.p;
+        v.csc_src = csc_src.p;
+        v.vals = vals.p;
+        v.c = c.p;
+        v.lb = lb.p;
+        v.ub = ub.p;
+        v.rl = rl.p;
+        v.ru = ru.p;
+        v.A = A.p;
+        v.AT = AT.p;
+        v.dr = dr.p;
+        v.dc = dc.p;
+        v.sr = sr.p;
+        v.scf = scf.p;
+        v.cs = cs.p;
+        v.lbs = lbs.p;
+        v.ubs = ubs.p;
+        v.rls = rls.p;
+        v.rus = rus.p;
+        v.x = x.p;
+        v.xa = xa.p;
+        v.xp = xp.p;
+        v.xbar = xbar.p;
+        v.gy = gy.p;
+        v.gyp = gyp.p;
+        v.y = y.p;
+        v.ya = ya.p;
+        v.yp = yp.p;
+        v.ray = ray.p;
+        v.xo = xo.p;
+        v.yo = yo.p;
+        v.dlo = dlo.p;
+        v.dup = dup.p;
+        v.partials = partials.p;
+        v.state = state.p;
+        v.prm = prm.p;
+        v.n_active = n_active.p;
+        return v;
+    }
+
+    static unsigned ew_grid(int64_t cnt) {
+        return (unsigned)std::max<int64_t>(1, std::min<int64_t>((cnt + 1023) / 1024, kSMs * 16));
+    }
+
+    int precondition(int ruiz_iters, int warm) {
+        LpView v = view();
+        const Geo gr = geo_for(m, B), gc = geo_for(n, B), gm = geo_for(std::max(n, m), B);
+        const int64_t nB = (int64_t)n * B, mB = (int64_t)m * B;
+        ASM_KL(k_fill<<<ew_grid(mB), 1024, 0, stream>>>(dr.p, 1.0, mB));
+        ASM_KL(k_fill<<<ew_grid(nB), 1024, 0, stream>>>(dc.p, 1.0, nB));
+        for (int it = 0; it <= ruiz_iters; ++it) {
+            if (it == ruiz_iters) {  // last pass: Pock-Chambolle (alpha = 1): 1-norms
+                ASM_KB2(k_ruiz_rows, true, gr, v);
+                ASM_KB2(k_ruiz_cols, true, gc, v);
+            } else {
+                ASM_KB2(k_ruiz_rows, false, gr, v);
+                ASM_KB2(k_ruiz_cols, false, gc, v);
+            }
+            ASM_KL(k_mul_inplace<<<ew_grid(mB), 1024, 0, stream>>>(dr.p, sr.p, mB));
+            ASM_KL(k_mul_inplace<<<ew_grid(nB), 1024, 0, stream>>>(dc.p, scf.p, nB));
+        }
+        ASM_KB(k_build_scaled_csr, gr, v);
+        ASM_KB(k_build_scaled_csc, gc, v);
+        ASM_KB(k_prepare_cols, gc, v);
+        ASM_KB(k_prepare_rows, gr, v);
+        ASM_KL(k_init_state<<<B, kFinalThreads, 0, stream>>>(v));
+        ASM_KB(k_prepare_finish, gm, v, warm);
+        if (B > Buser) ASM_KL(k_mark_padding<<<(B - Buser + 127) / 128, 128, 0, stream>>>(state.p, Buser, B));
+        ASM_CK(cudaGetLastError());
+        return ASM_OK;
+    }
+
+    // enqueue `steps` iterations; the first and the last are check steps
+    void enqueue_block(int steps) {
+        LpView v = view();
+        const Geo gr = geo_for(m, B), gc = geo_for(n, B), gm = geo_for(std::max(n, m), B);
+        for (int j = 0; j < steps; ++j) {
+            if (j == 0 || j == steps - 1) {
+                ASM_KB2(k_primal, true, gc, v, j);
+                ASM_KB2(k_dual, true, gr, v, j);
+                ASM_KB(k_dual_resid, gc, v);
+                ASM_KB(k_ray_rows, gr, v);
+                ASM_KB(k_ray_cols, gc, v);
+                ASM_KL(k_store_kstep<<<(B + 127) / 128, 128, 0, stream>>>(state.p, kstep.p, j, B));
+                ASM_KL(k_decide<<<B, kFinalThreads, 0, stream>>>(v, j, steps));
+                ASM_KB(k_apply, gm, v, kstep.p);
+                ASM_KL(k_after_apply<<<(B + 127) / 128, 128, 0, stream>>>(state.p, B));
+            } else {
+                ASM_KB2(k_primal, false, gc, v, j);
+                ASM_KB2(k_dual, false, gr, v, j);
+            }
+        }
+    }
+
+    int build_graph(int steps) {
+        if (graph_exec && graph_steps == steps) return ASM_OK;
+        if (graph_exec) {
+            cudaGraphExecDestroy(graph_exec);
+            graph_exec = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        const int64_t keep = launches;
+        ASM_CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        enqueue_block(steps);
+        cudaError_t e = cudaStreamEndCapture(stream, &g);
+        launches_per_graph = launches - keep;
+        launches = keep;
+        ASM_CK(e);
+        ASM_CK(cudaGraphInstantiate(&graph_exec, g, 0));
+        cudaGraphDestroy(g);
+        graph_steps = steps;
+        return ASM_OK;
+    }
+
+    int solve(const asm_lp_params &P, asm_lp_info *info) {
+        DevParams dp;
+        dp.eps_rel = P.eps_rel;
+        dp.eps_infeas = P.eps_infeas;
+        dp.b_suf = P.restart_sufficient;
+        dp.b_nec = P.restart_necessary;
+        dp.b_art = P.restart_artificial;
+        dp.kp = P.pid_kp;
+        dp.ki = P.pid_ki;
+        dp.kd = P.pid_kd;
+        dp.verbose = P.verbose;
+        int *flag = (int *)pin_flag.p;
+        DevParams *pdp = (DevParams *)((char *)pin_flag.p + 16);
+        static_assert(sizeof(DevParams) + 16 <= 128, "pinned flag area too small");
+        ASM_TRY(pin_flag.reserve(128));
+        flag = (int *)pin_flag.p;
+        pdp = (DevParams *)((char *)pin_flag.p + 16);
+        *pdp = dp;
+        *flag = Buser;
+        ASM_CK(cudaMemcpyAsync(prm.p, pdp, sizeof dp, cudaMemcpyHostToDevice, stream));
+        ASM_CK(cudaMemcpyAsync(n_active.p, flag, sizeof(int), cudaMemcpyHostToDevice, stream));
+        ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && has_solution) ? 1 : 0));
+        const int steps = std::max(2, (int)P.check_every);
+        ASM_TRY(build_graph(steps));
+        ASM_CK(cudaEventRecord(ev0, stream));
+        int64_t it = 0;
+        while (it < P.max_iter) {
+            ASM_CK(cudaGraphLaunch(graph_exec, stream));
+            launches += launches_per_graph;
+            it += steps;
+            ASM_CK(cudaMemcpyAsync(flag, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            ASM_CK(cudaStreamSynchronize(stream));
+            if (*flag <= 0) break;
+        }
+        ASM_CK(cudaEventRecord(ev1, stream));
+        LpView v = view();
+        const Geo gm = geo_for(std::max(n, m), B);
+        ASM_KB(k_finalize, gm, v);
+        ASM_CK(cudaMemcpyAsync(host_state.data(), state.p, sizeof(ScenState) * B, cudaMemcpyDeviceToHost, stream));
+        std::vector<double> hc0(B, 0.0);
+        ASM_CK(cudaMemcpyAsync(hc0.data(), c0.p, sizeof(double) * B, cudaMemcpyDeviceToHost, stream));
+        ASM_CK(cudaStreamSynchronize(stream));
+        float ms = 0.f;
+        ASM_CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        last_loop_ms = ms;
+        last_iters = 0;
+        for (int s = 0; s < Buser; ++s) {
+            ScenState &st = host_state[s];
+            if (st.status < 0) st.status = ASM_LP_ITERATION_LIMIT;
+            last_iters = std::max<int64_t>(last_iters, st.total);
+            if (info) {
+                info[s].status = st.status;
+                info[s].restarts = st.restarts;
+                info[s].iterations = st.total;
+                info[s].objective = st.pobj + hc0[s];
+                info[s].dual_objective = st.dobj + hc0[s];
+                info[s].primal_residual = st.pres;
+                info[s].dual_residual = st.dres;
+                info[s].gap = st.gap;
+            }
+        }
+        has_solution = true;
+        return ASM_OK;
+    }
+};
+
+}  // namespace asmb

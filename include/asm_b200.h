@@ -1,0 +1,189 @@
+/*
+ * asm_b200.h — C ABI of the B200-native sub-LP engine for sequential linear programming.
+ *
+ * This is the drop-in boundary for the hot path of exanauts/ActiveSetMethods (reference tree
+ * /root/reference, all citations relative to it).  The reference reaches its LP solver through the
+ * `"external_optimizer"` MathOptInterface hook (src/parameters.jl:7, instantiated at
+ * src/algorithms/slp.jl:32) and pushes / reads the sub-LP one scalar at a time
+ * (src/algorithms/subproblem.jl:51-215, :229-542).  A Julia MOI shim binds the functions below with
+ * `ccall`; Python/ctypes binds them for the tests.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all arrays are caller-owned host memory unless a name says `dev`;
+ *   - every function returns 0 on success or a negative ASM_E_* code; no C++ exception crosses the ABI;
+ *     `asm_last_error()` returns a thread-local message for the last failure;
+ *   - +-infinity bounds are IEEE infinities;
+ *   - batch: a handle created with `batch = B` holds B independent LPs that share one sparsity pattern.
+ *     Host arrays of a batch are laid out scenario-major, `a[s * len + i]` (B contiguous vectors);
+ *   - one CUDA stream and one host thread per handle; calls on a handle block until the result is in
+ *     host memory unless stated otherwise.
+ *
+ * There is no CPU fallback: every entry point that computes fails with ASM_E_CUDA when no sm_100-class
+ * device is available.
+ */
+#ifndef ASM_B200_H
+#define ASM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ------------------------------------------------------------------------------------ */
+#define ASM_OK 0
+#define ASM_E_INVALID (-1)  /* bad argument (null pointer, negative size, index out of range)            */
+#define ASM_E_CUDA (-2)     /* CUDA runtime error / no device                                            */
+#define ASM_E_FREE_ROW (-3) /* a row with both bounds infinite: the reference builder pushes no row for  */
+                            /* it and breaks (subproblem.jl:143-197), so it is rejected here             */
+#define ASM_E_STATE (-4)    /* call out of order (e.g. solve before update)                              */
+
+/* ---- LP termination status (the subset of MOI.TerminationStatus the reference branches on,
+ *      subproblem.jl:491-539) ------------------------------------------------------------------------- */
+#define ASM_LP_OPTIMAL 0
+#define ASM_LP_INFEASIBLE 1
+#define ASM_LP_DUAL_INFEASIBLE 2
+#define ASM_LP_ITERATION_LIMIT 3
+#define ASM_LP_NUMERICAL_ERROR 4
+
+const char *asm_last_error(void);
+/* number of visible CUDA devices (0 if none); never fails */
+int asm_device_count(void);
+const char *asm_version(void);
+
+/* ---- solver parameters ------------------------------------------------------------------------------- */
+typedef struct asm_lp_params {
+    double eps_rel;        /* relative KKT tolerance: primal residual, dual residual and gap (default 1e-8) */
+    double eps_infeas;     /* Farkas-certificate tolerance (default 1e-9)                                   */
+    int64_t max_iter;      /* PDHG iteration limit per LP (default 2 000 000)                               */
+    int32_t check_every;   /* KKT / restart evaluation period in iterations (default 64)                   */
+    int32_t ruiz_iters;    /* Ruiz equilibration passes before Pock-Chambolle (default 10)                 */
+    int32_t warm_start;    /* 1: start from the previous solve's (x, y) of this handle (default 0)         */
+    int32_t verbose;       /* 1: print one line per restart check of scenario 0 to stderr                  */
+    double restart_sufficient; /* 0.2  */
+    double restart_necessary;  /* 0.8  */
+    double restart_artificial; /* 0.36 */
+    double pid_kp, pid_ki, pid_kd; /* primal-weight controller (0.99, 0.96, 0.0)                            */
+    double reserved[4];
+} asm_lp_params;
+void asm_lp_default_params(asm_lp_params *p);
+
+/* per-LP solve report (arrays of length batch) */
+typedef struct asm_lp_info {
+    int32_t status;     /* ASM_LP_*                                  */
+    int32_t restarts;
+    int64_t iterations;
+    double objective;   /* c'x + c0 at the returned point            */
+    double dual_objective;
+    double primal_residual; /* ||Kx - proj(Kx)||_2, unscaled         */
+    double dual_residual;   /* ||c - K'y - r||_2, unscaled           */
+    double gap;             /* |pobj - dobj|                         */
+} asm_lp_info;
+
+/* =======================================================================================================
+ * 1. Generic LP handle:   min c'x + c0   s.t.  rl <= K x <= ru,  lb <= x <= ub.
+ *    What a GLPK-replacing MOI optimizer needs (the MOI calls listed in SURVEY.md App. B,
+ *    subproblem.jl:54-213 build, :252-483 update, :490 solve, :491-520 read-back).
+ * ===================================================================================================== */
+typedef struct asm_lp asm_lp;
+
+/* pattern is 0-based CSR, uploaded once (MOI add_variables/add_constraint, subproblem.jl:75-213) */
+int asm_lp_create(int32_t n_cols, int32_t n_rows, int64_t nnz, const int64_t *row_ptr, const int32_t *col_idx,
+                  int32_t batch, int32_t device, asm_lp **out);
+void asm_lp_destroy(asm_lp *h);
+/* MOI.modify(row, ScalarCoefficientChange) for the whole pattern (subproblem.jl:438-457); vals[batch][nnz] */
+int asm_lp_set_matrix_values(asm_lp *h, const double *vals);
+/* MOI.modify(ObjectiveFunction, ...) (subproblem.jl:252-272, :385-405); c[batch][n_cols], c0[batch] */
+int asm_lp_set_objective(asm_lp *h, const double *c, const double *c0);
+/* MOI.set(ConstraintSet, bound ci) (subproblem.jl:427-434) */
+int asm_lp_set_col_bounds(asm_lp *h, const double *lb, const double *ub);
+/* MOI.set(ConstraintSet, row ci) (subproblem.jl:461-484) */
+int asm_lp_set_row_bounds(asm_lp *h, const double *rl, const double *ru);
+/* MOI.optimize! (subproblem.jl:490); info[batch] */
+int asm_lp_solve(asm_lp *h, const asm_lp_params *params, asm_lp_info *info);
+/* MOI.get(VariablePrimal) (subproblem.jl:502-505); x[batch][n_cols] */
+int asm_lp_get_primal(asm_lp *h, double *x);
+/* MOI.get(ConstraintDual) on rows (subproblem.jl:510-515): >=0 lower side active, <=0 upper side */
+int asm_lp_get_row_dual(asm_lp *h, double *y);
+/* MOI.get(ConstraintDual) on the two bound constraints of every column (subproblem.jl:519-520):
+ * dual_lb >= 0 (GreaterThan), dual_ub <= 0 (LessThan); either pointer may be NULL */
+int asm_lp_get_col_dual(asm_lp *h, double *dual_lb, double *dual_ub);
+/* warm start for the next solve (used when params.warm_start = 1); either pointer may be NULL */
+int asm_lp_set_start(asm_lp *h, const double *x, const double *y);
+
+/* =======================================================================================================
+ * 2. SLP fast path: the whole per-iteration sub-LP of the reference in three calls.
+ *    Replaces compute_jacobian_matrix (common.jl:12-20), LpData (slp.jl:8-21), create_model!
+ *    (subproblem.jl:51-215) and sub_optimize! (subproblem.jl:229-542).
+ * ===================================================================================================== */
+typedef struct asm_slp asm_slp;
+
+/* Model (model.jl:1-61) + create_model!: bounds, and the COO Jacobian pattern j_str as 1-based
+ * (row, col) pairs with duplicates allowed (model.jl:10).  The pattern is analysed and uploaded once.
+ * x_L/x_U [n], g_L/g_U [m] are shared by all `batch` scenarios unless `per_scenario_bounds` != 0, in
+ * which case they are [batch][n] / [batch][m]. */
+int asm_slp_create(int32_t n, int32_t m, int64_t nnz_coo, const int64_t *j_row, const int64_t *j_col,
+                   const double *x_L, const double *x_U, const double *g_L, const double *g_U, int32_t batch,
+                   int32_t per_scenario_bounds, int32_t device, asm_slp **out);
+void asm_slp_destroy(asm_slp *h);
+
+/* sizes of the assembled (deduplicated) Jacobian and of the LP in reference form
+ * (subproblem.jl:75-112: n + slacks columns; m + |adj| rows) */
+int asm_slp_sizes(asm_slp *h, int64_t *nnz_csr, int32_t *lp_cols, int32_t *lp_rows);
+/* the CSR pattern and, after an update, the values of the assembled Jacobian of scenario `s`
+ * (bit-exact restatement of common.jl:12-20; duplicates summed in j_str order from 0.0).
+ * row_ptr[m+1], col_idx[nnz_csr] 0-based, vals[nnz_csr]; any pointer may be NULL */
+int asm_slp_get_csr(asm_slp *h, int32_t s, int64_t *row_ptr, int32_t *col_idx, double *vals);
+
+/* eval_functions! hand-over (slp.jl:186-191) + the data push of sub_optimize! (subproblem.jl:248-484):
+ * x_k[batch][n], f[batch], df[batch][n], E[batch][m], dE[batch][nnz_coo] (j_str order), delta[batch],
+ * feasibility (shared flag: 0 normal phase, 1 feasibility restoration).
+ * Copies through pinned staging, assembles the CSR, builds column / row / slack bounds on the device. */
+int asm_slp_update(asm_slp *h, const double *x_k, const double *f, const double *df, const double *E,
+                   const double *dE, const double *delta, int32_t feasibility);
+/* MOI.optimize! on the current sub-LP (subproblem.jl:490); device-resident, no host copies except the
+ * convergence flags.  info[batch] may be NULL. */
+int asm_slp_solve(asm_slp *h, const asm_lp_params *params, asm_lp_info *info);
+/* read-back of subproblem.jl:491-541: p[batch][n] (Xsol), lambda[batch][m] (row duals, range rows
+ * summed), mult_x_U/mult_x_L[batch][n] (bound duals masked to the original bounds, :522-529),
+ * p_slack[batch][m][2] (second entry 0 for one-slack rows; all 0 in the normal phase), status[batch].
+ * INFEASIBLE => zeros (:532-536).  Any output pointer may be NULL. */
+int asm_slp_extract(asm_slp *h, double *p, double *lambda, double *mult_x_U, double *mult_x_L,
+                    double *p_slack, int32_t *status);
+/* update + solve + extract in one call: the reference's sub_optimize!(slp, delta) (slp.jl:23-47) */
+int asm_slp_sub_optimize(asm_slp *h, const double *x_k, const double *f, const double *df, const double *E,
+                         const double *dE, const double *delta, int32_t feasibility,
+                         const asm_lp_params *params, double *p, double *lambda, double *mult_x_U,
+                         double *mult_x_L, double *p_slack, int32_t *status, asm_lp_info *info);
+
+/* ---- merit / KKT reductions on the device (they use x_k, df, E, J of the last asm_slp_update and the
+ *      multipliers / step of the last solve unless host arrays are given) ------------------------------ */
+/* norm_violations (common.jl:75-98): p_norm = 0 -> infinity norm, 1 -> 1-norm, 2 -> 2-norm.
+ * E[batch][m], x[batch][n] host arrays; out[batch] */
+int asm_slp_norm_violations(asm_slp *h, const double *E, const double *x, int32_t p_norm, double *out);
+/* KT_residuals (common.jl:35-44) with the Jacobian of the last update: df, lambda, mult_x_U, mult_x_L */
+int asm_slp_kt_residuals(asm_slp *h, const double *df, const double *lambda, const double *mult_x_U,
+                         const double *mult_x_L, double *out);
+/* norm_complementarity (common.jl:51-68), infinity norm */
+int asm_slp_norm_complementarity(asm_slp *h, const double *E, const double *lambda, double *out);
+/* row 2-norms of the assembled Jacobian (used by compute_nu!, slp.jl:54-66, and KT_residuals) */
+int asm_slp_row_norms(asm_slp *h, double *out /* [batch][m] */);
+/* compute_phi (slp.jl:79-115) constraint part: sum_i nu_i * viol_i(E_trial) in the normal phase;
+ * in feasibility restoration the shifted form of :84-103 with the slacks of the last extract.
+ * base[batch] is f(x + alpha p) (normal) or prim_infeas (restoration); E_trial is g(x + alpha p) */
+int asm_slp_merit_phi(asm_slp *h, const double *base, const double *E_trial, const double *nu,
+                      const double *alpha, int32_t feasibility, double *out);
+/* compute_derivative (slp.jl:122-147) with the df, E of the last update and the p / slacks of the last solve */
+int asm_slp_merit_derivative(asm_slp *h, const double *nu, int32_t feasibility, double *out);
+
+/* ---- instrumentation --------------------------------------------------------------------------------- */
+/* kernels launched by this handle's solver since creation (all of them this library's own) */
+int64_t asm_slp_launch_count(asm_slp *h);
+/* device time (ms, CUDA events on the handle's stream) of the PDHG loop of the last asm_slp_solve and
+ * the total PDHG iterations it ran (max over the batch) */
+int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASM_B200_H */

@@ -1,0 +1,183 @@
+"""GPU parity: the CUDA sub-LP path (through the C ABI) against the CPU oracle on the same linearisations.
+
+Bars (BASELINE.json north_star): CSR assembly bit-exact; per sub-LP objective <= 1e-6 relative, primal and
+dual feasibility <= 1e-6; LP status identical."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import problem, record_sublps, lp_feasibility, dual_feasibility
+from oracle import slp_oracle as so
+from test_oracle_pins import case3_network, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+OBJ_RTOL = 1e-6
+FEAS_TOL = 1e-6
+
+
+def _check_lp(lp, ref, pat, d, n, m):
+    """Solve one recorded linearisation on the GPU and compare with the oracle's simplex solve."""
+    vals = pat.assemble(d["dE"])
+    p, lam, mu_u, mu_l, slack, status = lp.sub_optimize(d["x"], d["f"], d["df"], d["E"], d["dE"], d["delta"], d["fr"])
+    rp, ci, v = lp.jacobian_csr()
+    assert np.array_equal(v, vals), "device CSR values are not bit-identical to compute_jacobian_matrix"
+    ref_out = ref.solve(vals, d["df"], d["f"], d["E"], d["x"], d["delta"], d["fr"])
+    assert status == ref_out[5], f"LP status {status} != oracle {ref_out[5]} (fr={d['fr']})"
+    info = lp.last_info[0]
+    if status != so.OPTIMAL:
+        assert not p.any() and not lam.any()
+        return info
+    K, cost, off, lb, ub, rl, ru = ref.last_lp
+    obj_ref = ref.last_objective
+    assert abs(info["objective"] - obj_ref) <= OBJ_RTOL * max(1.0, abs(obj_ref)), (info, obj_ref)
+    # primal feasibility of the full LP point (p + slacks in the reference's column layout)
+    xfull = np.zeros(K.shape[1])
+    xfull[:n] = p
+    if d["fr"]:
+        xfull[ref.s1] = slack[:, 0]
+        xfull[ref.s2[ref.two]] = slack[ref.two, 1]
+    assert lp_feasibility(K, xfull, lb, ub, rl, ru) <= FEAS_TOL
+    assert abs(cost @ xfull + off - info["objective"]) <= 1e-9 * max(1.0, abs(obj_ref))
+    # dual feasibility: lambda (range rows already summed) against the J block
+    J = pat.matrix(vals)
+    c = np.zeros(n) if d["fr"] else d["df"]
+    assert dual_feasibility(J, c, p, lam, lb[:n], ub[:n], tol=1e-7) <= FEAS_TOL * max(1.0, np.max(np.abs(c)))
+    # multipliers only where the *original* bound is active (subproblem.jl:522-529)
+    assert np.all(mu_u[p < (ref.v_ub - d["x"])] == 0.0) and np.all(mu_l[p > (ref.v_lb - d["x"])] == 0.0)
+    assert np.all(mu_u <= 0.0) and np.all(mu_l >= 0.0)
+    return info
+
+
+@pytest.mark.parametrize("name", ["toy", "case3", "case9", "case9tr"])
+def test_golden_sublps(gpu, name):
+    """Committed fixtures (tests/golden/sublp_*.npz): status and objective of every recorded sub-LP."""
+    from activesetmethods_b200.sublp import SubLp
+    g = np.load(os.path.join(GOLDEN, f"sublp_{name}.npz"))
+    from activesetmethods_b200.examples import acopf, small_nlps
+    pr = {"toy": small_nlps.ToyNlp, "case3": lambda: acopf.AcopfModel(case3_network()),
+          "case9": lambda: acopf.AcopfModel(acopf.case9()), "case9tr": lambda: acopf.AcopfModel(acopf.case9())}[name]()
+    lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U)
+    for k in range(len(g["f"])):
+        out = lp.sub_optimize(g["x"][k], g["f"][k], g["df"][k], g["E"][k], g["dE"][k], g["delta"][k], bool(g["fr"][k]))
+        assert out[5] == int(g["status"][k]), (k, out[5], int(g["status"][k]))
+        if out[5] == 0:
+            obj = lp.last_info[0]["objective"]
+            assert abs(obj - g["objective"][k]) <= OBJ_RTOL * max(1.0, abs(g["objective"][k])), (k, obj)
+    lp.close()
+
+
+@pytest.mark.parametrize("name,alg,limit", [("toy", "Line Search", 14), ("hs071", "Line Search", 6),
+                                            ("case9", "Line Search", 6), ("case9", "Trust Region", 6),
+                                            ("case118", "Line Search", 3), ("case118", "Trust Region", 3)])
+def test_sublp_parity_live(gpu, name, alg, limit):
+    from activesetmethods_b200.sublp import SubLp
+    pr = problem(name)
+    slp, lps = record_sublps(pr, alg, max_iter=40, limit=limit)
+    pat = so.JacobianPattern(pr.m, pr.n, pr.j_str)
+    lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U)
+    for d in lps:
+        ref = so.SubLp(pat, pr.g_L, pr.g_U, pr.x_L, pr.x_U)
+        _check_lp(lp, ref, pat, d, pr.n, pr.m)
+    lp.close()
+
+
+def test_assembly_bit_exact_with_duplicates(gpu):
+    """common.jl:12-20 with duplicate COO entries, wide dynamic range, signed zeros; batch of 40 scenarios."""
+    from activesetmethods_b200.examples import small_nlps
+    from activesetmethods_b200.sublp import SubLp
+    pr = small_nlps.RandomNlp()
+    pat = so.JacobianPattern(pr.m, pr.n, pr.j_str)
+    assert pat.nnz < len(pr.j_str)
+    rng = np.random.default_rng(0)
+    for B in (1, 40):
+        lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, batch=B)
+        nz = len(pr.j_str)
+        dE = rng.standard_normal((B, nz)) * 10.0 ** rng.integers(-12, 12, (B, nz))
+        dE[:, ::7] = -0.0
+        x = np.tile(pr.x0, (B, 1))
+        lp.update(x, np.zeros(B), np.zeros((B, pr.n)), np.zeros((B, pr.m)), dE, 1.0, False)
+        for s in range(B):
+            rp, ci, v = lp.jacobian_csr(s)
+            ref = pat.assemble(dE[s])
+            assert np.array_equal(rp, pat.row_ptr) and np.array_equal(ci, pat.cols)
+            assert np.array_equal(v, ref) and np.array_equal(np.signbit(v), np.signbit(ref))
+        lp.close()
+
+
+def test_empty_and_error_paths(gpu):
+    from activesetmethods_b200 import capi
+    from activesetmethods_b200.sublp import SubLp
+    # free row -> rejected like the reference builder (subproblem.jl:143-197 pushes no row)
+    with pytest.raises(capi.AsmError) as e:
+        SubLp(2, 1, np.array([[1, 1]]), [-1, -1], [1, 1], [-np.inf], [np.inf])
+    assert e.value.code == capi.E_FREE_ROW
+    # out-of-range pattern entry
+    with pytest.raises(capi.AsmError) as e:
+        SubLp(2, 1, np.array([[2, 1]]), [-1, -1], [1, 1], [0.0], [1.0])
+    assert e.value.code == capi.E_INVALID
+    # solve before update
+    lp = SubLp(2, 1, np.array([[1, 1], [1, 2]]), [-1, -1], [1, 1], [0.0], [1.0])
+    with pytest.raises(capi.AsmError) as e:
+        lp.solve()
+    assert e.value.code == capi.E_STATE
+    # m = 0: a pure box LP  min df'p, |p| <= delta
+    lp0 = SubLp(3, 0, np.zeros((0, 2), dtype=np.int64), [-5, -5, -5], [5, 5, 5], [], [])
+    p, lam, mu_u, mu_l, slack, status = lp0.sub_optimize(np.zeros(3), 0.0, np.array([1.0, -2.0, 0.0]), [], [], 0.5)
+    assert status == 0 and np.allclose(p[:2], [-0.5, 0.5]) and abs(lp0.last_info[0]["objective"] + 1.5) < 1e-7
+
+
+def test_batch_matches_single(gpu):
+    """A batch of perturbed case9 linearisations gives, per scenario, what the single-LP path gives."""
+    from activesetmethods_b200.examples import acopf
+    from activesetmethods_b200.sublp import SubLp
+    net = acopf.case9()
+    B = 5
+    mdls = [acopf.AcopfModel(acopf.perturb_loads(net, s + 1)) for s in range(B)]
+    m0 = mdls[0]
+    gL = np.array([m.g_L for m in mdls]); gU = np.array([m.g_U for m in mdls])
+    xL = np.array([m.x_L for m in mdls]); xU = np.array([m.x_U for m in mdls])
+    x = np.array([np.clip(m.x0, m.x_L, m.x_U) for m in mdls])
+    f = np.array([m.eval_f(xx) for m, xx in zip(mdls, x)])
+    df = np.array([m.eval_grad_f(xx, np.zeros(m.n)) for m, xx in zip(mdls, x)])
+    E = np.array([m.eval_g(xx, np.zeros(m.m)) for m, xx in zip(mdls, x)])
+    dE = np.array([m.eval_jac_g(xx, "eval", None, None, np.zeros(m.nnz)) for m, xx in zip(mdls, x)])
+    lpb = SubLp(m0.n, m0.m, m0.j_str, xL, xU, gL, gU, batch=B)
+    pb, lamb, _, _, _, stb = lpb.sub_optimize(x, f, df, E, dE, 1000.0, False)
+    pat = so.JacobianPattern(m0.m, m0.n, m0.j_str)
+    for s in range(B):
+        ref = so.SubLp(pat, gL[s], gU[s], xL[s], xU[s])
+        ref.solve(pat.assemble(dE[s]), df[s], f[s], E[s], x[s], 1000.0, False)
+        assert stb[s] == 0
+        obj = lpb.last_info[s]["objective"]
+        assert abs(obj - ref.last_objective) <= OBJ_RTOL * max(1.0, abs(ref.last_objective)), (s, obj)
+    lpb.close()
+
+
+def test_generic_lp_against_highs(gpu):
+    """B200LP as a general external LP optimizer: random feasible bounded LPs against HiGHS."""
+    import scipy.sparse as sp
+    from activesetmethods_b200.sublp import B200LP
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        n, m = 30 + 10 * trial, 20 + 5 * trial
+        K = sp.random(m, n, density=0.2, random_state=trial, format="csr")
+        K.data = rng.standard_normal(len(K.data))
+        x0 = rng.uniform(-1, 1, n)
+        Kx = K @ x0
+        rl = Kx - rng.uniform(0, 1, m); ru = Kx + rng.uniform(0, 1, m)
+        rl[::3] = ru[::3] = Kx[::3]
+        rl[1::5] = -np.inf
+        lb = np.full(n, -2.0); ub = np.full(n, 2.0)
+        c = rng.standard_normal(n)
+        eng = so.HighsLp()
+        st, xr, yr, dr, obj = eng.solve(K.tocsc(), c, 0.25, lb, ub, rl, ru)
+        assert st == so.OPTIMAL
+        lp = B200LP(n, m, K.indptr, K.indices)
+        lp.set_matrix_values(K.data); lp.set_objective(c, 0.25); lp.set_col_bounds(lb, ub); lp.set_row_bounds(rl, ru)
+        info = lp.optimize()[0]
+        assert info["status"] == 0
+        assert abs(info["objective"] - obj) <= OBJ_RTOL * max(1.0, abs(obj))
+        assert lp_feasibility(K, lp.primal(), lb, ub, rl, ru) <= FEAS_TOL
+        lp.close()
