@@ -779,8 +779,8 @@ void asm_lp_default_params(asm_lp_params *p) {
     p->restart_sufficient = 0.2;
     p->restart_necessary = 0.8;
     p->restart_artificial = 0.36;
-    p->pid_kp = 0.99;
-    p->pid_ki = 0.96;
+    p->pid_kp = 0.5;
+    p->pid_ki = 0.0;
     p->pid_kd = 0.0;
 }
 

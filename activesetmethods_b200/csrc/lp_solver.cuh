@@ -22,7 +22,7 @@
 namespace asmb {
 
 struct ScenState {
-    double omega, eta, sb, sc;
+    double omega, omega0, eta, sb, sc;
     double nq_un, nc_un;
     double r0, r_prev, e_sum, e_prev;
     double pobj, dobj, pres, dres, gap;
@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kFinalThreads) k_init_state(LpView v) {
         st.sc = 1.0 / (sqrt(c2) + 1.0);
         const double nc = sqrt(c2) * st.sc, nq = sqrt(q2) * st.sb;
         st.omega = (nc > 0.0 && nq > 0.0) ? nc / nq : 1.0;
+        st.omega0 = st.omega;
         st.eta = 0.998;  // ||A||_2 <= 1 after Pock-Chambolle (alpha = 1) scaling
         st.nq_un = sqrt(qun2);
         st.nc_un = sqrt(cun2);
@@ -461,13 +462,21 @@ __global__ void __launch_bounds__(kFinalThreads) k_decide(LpView v, int jit, int
         }
         st.r_prev = r;
         if (restart) {
+            // primal weight: PID controller on log(omega * |dx| / |dy|); the default gains (0.5, 0, 0) are the
+            // PDLP rule omega <- sqrt(omega * |dy| / |dx|).  Degenerate moves or a runaway weight fall back to
+            // the initial one.
             const double ddx = sqrt(q[Q_DXA2]), ddy = sqrt(q[Q_DYA2]);
-            if (ddx > 1e-300 && ddy > 1e-300) {
+            if (ddx > 1e-16 && ddy > 1e-16) {
                 const double e = log(st.omega * ddx / ddy);
                 st.e_sum += e;
                 const double dlog = -(P.kp * e + P.ki * st.e_sum + P.kd * (e - st.e_prev));
                 st.omega = exp(log(st.omega) + dlog);
                 st.e_prev = e;
+            }
+            if (!(st.omega > st.omega0 * 1e-8 && st.omega < st.omega0 * 1e8)) {
+                st.omega = st.omega0;
+                st.e_sum = 0.0;
+                st.e_prev = 0.0;
             }
             st.restarts += 1;
             st.r_prev = INFINITY;

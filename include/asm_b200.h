@@ -63,7 +63,7 @@ typedef struct asm_lp_params {
     double restart_sufficient; /* 0.2  */
     double restart_necessary;  /* 0.8  */
     double restart_artificial; /* 0.36 */
-    double pid_kp, pid_ki, pid_kd; /* primal-weight controller (0.99, 0.96, 0.0)                            */
+    double pid_kp, pid_ki, pid_kd; /* primal-weight controller on log(w |dx|/|dy|); (0.5, 0, 0) = PDLP rule  */
     double reserved[4];
 } asm_lp_params;
 void asm_lp_default_params(asm_lp_params *p);

@@ -26,7 +26,19 @@ for kv in sys.argv[4:]:
     opts[k] = float(v) if ("." in v or "e" in v) else int(v)
 pr = problem(name)
 t = time.time()
-slp, lps = record_sublps(pr, alg, max_iter=40, limit=limit)
+NOREF = bool(int(os.environ.get("NOREF", "0")))
+if limit == 0:   # first linearisation only, no oracle SLP run (big cases)
+    x = np.clip(pr.x0, pr.x_L, pr.x_U)
+    lps = [dict(x=x, f=pr.eval_f(x), df=pr.eval_grad_f(x, np.zeros(pr.n)), E=pr.eval_g(x, np.zeros(pr.m)),
+                dE=pr.eval_jac_g(x, "eval", None, None, np.zeros(len(pr.j_str))),
+                delta=1000.0 if alg == "Line Search" else 0.4, fr=False)]
+
+    class _S:
+        ret = iter = -1
+        obj_val = float("nan")
+    slp = _S()
+else:
+    slp, lps = record_sublps(pr, alg, max_iter=40, limit=limit)
 print(f"{name} {alg}: n {pr.n} m {pr.m} nnz {len(pr.j_str)}; oracle SLP ret {slp.ret} iters {slp.iter} obj {slp.obj_val:.6f} "
       f"in {time.time() - t:.2f}s", flush=True)
 pat = so.JacobianPattern(pr.m, pr.n, pr.j_str)
@@ -34,7 +46,7 @@ lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, **opts)
 for k, d in enumerate(lps):
     ref = so.SubLp(pat, pr.g_L, pr.g_U, pr.x_L, pr.x_U)
     t0 = time.time()
-    ro = ref.solve(pat.assemble(d["dE"]), d["df"], d["f"], d["E"], d["x"], d["delta"], d["fr"])
+    ro = (None,) * 5 + (-1,) if NOREF else ref.solve(pat.assemble(d["dE"]), d["df"], d["f"], d["E"], d["x"], d["delta"], d["fr"])
     t_ref = time.time() - t0
     t0 = time.time()
     out = lp.sub_optimize(d["x"], d["f"], d["df"], d["E"], d["dE"], d["delta"], d["fr"])

@@ -57,7 +57,8 @@ def power_norm(A, iters=40, seed=0):
 
 def solve(K, c, lb, ub, rl, ru, eps=1e-6, max_iter=200000, check_every=64, verbose=False,
           x0=None, y0=None, kp=0.99, ki=0.96, kd=0.0, reflect=1.0, eps_infeas=1e-8, omega0=None,
-          bound_obj_rescale=True, ruiz_iters=10, pc=True, b_suf=0.2, b_nec=0.8, b_art=0.36, clamp=None):
+          bound_obj_rescale=True, ruiz_iters=10, pc=True, b_suf=0.2, b_nec=0.8, b_art=0.36, clamp=None, i_smooth=1.0,
+          guard=0.0, power=False):
     K = sp.csr_matrix(K)
     m, n = K.shape
     A, dr, dc = ruiz_pc_scale(K, ruiz_iters, pc)
@@ -74,8 +75,9 @@ def solve(K, c, lb, ub, rl, ru, eps=1e-6, max_iter=200000, check_every=64, verbo
     lbs, ubs, rls, rus = lbs * sb, ubs * sb, rls * sb, rus * sb
     # x_s = sb * x/dc ; y_s = sc_ * y/dr
 
-    normA = 1.0 if pc else power_norm(A, 400) * 1.01  # Pock-Chambolle (alpha=1) guarantees ||A||_2 <= 1; power iteration under-estimates
+    normA = power_norm(A, 400) * 1.01 if (not pc or power) else 1.0  # Pock-Chambolle (alpha=1) guarantees ||A||_2 <= 1; power iteration under-estimates
     eta = 0.998 / normA if normA > 0 else 1.0
+    if verbose: print('normA', normA)
     nq = np.linalg.norm(np.concatenate([rls[np.isfinite(rls)], rus[np.isfinite(rus) & (rus != rls)]]))
     nc = np.linalg.norm(cs)
     omega = omega0 if omega0 else (nc / nq if (nc > 0 and nq > 0) else 1.0)
@@ -97,6 +99,7 @@ def solve(K, c, lb, ub, rl, ru, eps=1e-6, max_iter=200000, check_every=64, verbo
     e_prev = 0.0
     n_restart = 0
     hist = []
+    omega_init = omega; best_omega = omega; best_bal = INF
     status = "ITERATION_LIMIT"
     fin_lb, fin_ub = np.isfinite(lb), np.isfinite(ub)
     while total < max_iter:
@@ -179,14 +182,23 @@ def solve(K, c, lb, ub, rl, ru, eps=1e-6, max_iter=200000, check_every=64, verbo
             if restart:
                 ddx = np.linalg.norm(xp - xa)
                 ddy = np.linalg.norm(yp - ya)
-                if ddx > 1e-300 and ddy > 1e-300:
+                if guard > 0 and (ddx <= guard or ddy <= guard or omega < omega_init * 1e-5 or omega > omega_init * 1e5):
+                    omega = best_omega
+                    e_sum = 0.0
+                    e_prev = 0.0
+                elif ddx > 1e-300 and ddy > 1e-300:
                     e = math.log((math.sqrt(omega) * ddx) / (ddy / math.sqrt(omega)))
-                    e_sum = e_sum + e
+                    e_sum = i_smooth * e_sum + e
                     dlog = -(kp * e + ki * e_sum + kd * (e - e_prev))
                     if clamp:
                         dlog = max(-clamp, min(clamp, dlog))
                     omega = math.exp(math.log(omega) + dlog)
                     e_prev = e
+                rp_ = pres / (1 + nq_un); rd_ = dres / (1 + nc_un)
+                if rp_ > 0 and rd_ > 0:
+                    bal = abs(math.log10(rd_ / rp_))
+                    if bal < best_bal:
+                        best_bal = bal; best_omega = omega
                 xn, yn = xp.copy(), yp.copy()
                 xa, ya = xn.copy(), yn.copy()
                 k = 0
