@@ -28,7 +28,8 @@ class LpParams(C.Structure):
         ("check_every", C.c_int32), ("ruiz_iters", C.c_int32), ("warm_start", C.c_int32), ("verbose", C.c_int32),
         ("restart_sufficient", C.c_double), ("restart_necessary", C.c_double), ("restart_artificial", C.c_double),
         ("pid_kp", C.c_double), ("pid_ki", C.c_double), ("pid_kd", C.c_double),
-        ("reserved", C.c_double * 4),
+        ("engine", C.c_int32), ("group_size", C.c_int32),
+        ("reserved", C.c_double * 3),
     ]
 
 
@@ -85,6 +86,12 @@ SIGNATURES = {
     "asm_slp_merit_derivative": (C.c_int, [_VP, c_double_p, C.c_int32, c_double_p]),
     "asm_slp_launch_count": (C.c_int64, [_VP]),
     "asm_slp_last_solve_timing": (C.c_int, [_VP, c_double_p, c_int64_p]),
+    "asm_slp_engine_info": (C.c_int, [_VP, c_int32_p, c_int32_p, c_int32_p]),
+    "asm_slp_reassemble": (C.c_int, [_VP, C.c_int32]),
+    "asm_slp_extract_device": (C.c_int, [_VP]),
+    "asm_slp_timer_start": (C.c_int, [_VP]),
+    "asm_slp_timer_stop": (C.c_int, [_VP, c_double_p]),
+    "asm_slp_kernel_timing": (C.c_int, [_VP, C.c_int32, c_double_p, c_double_p]),
 }
 
 _lib = None

@@ -380,10 +380,13 @@ struct SlpHandle {
     bool solved = false, extracted = false;
     Pinned pin_small;
     int64_t own_launches = 0;
+    cudaEvent_t tev0 = nullptr, tev1 = nullptr;
 
     ~SlpHandle() {
         normal.reset();
         fr.reset();
+        if (tev0) cudaEventDestroy(tev0);
+        if (tev1) cudaEventDestroy(tev1);
         if (stream) cudaStreamDestroy(stream);
     }
     LpSolver *cur() { return phase == 1 ? fr.get() : normal.get(); }
@@ -1096,6 +1099,54 @@ int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations) 
     if (loop_ms) *loop_ms = h->h.cur()->last_loop_ms;
     if (iterations) *iterations = h->h.cur()->last_iters;
     return ASM_OK;
+}
+
+int asm_slp_engine_info(asm_slp *h, int32_t *engine, int32_t *group_size, int32_t *groups) {
+    if (!h) return fail(ASM_E_INVALID, "null handle");
+    if (!h->h.solved) return fail(ASM_E_STATE, "no solve yet");
+    LpSolver *lp = h->h.cur();
+    if (engine) *engine = lp->last_engine;
+    if (group_size) *group_size = lp->last_G;
+    if (groups) *groups = lp->last_groups;
+    return ASM_OK;
+}
+int asm_slp_reassemble(asm_slp *h, int32_t feasibility) {
+    if (!h) return fail(ASM_E_INVALID, "null handle");
+    if (h->h.phase < 0) return fail(ASM_E_STATE, "asm_slp_reassemble before asm_slp_update");
+    ASM_CK(cudaSetDevice(h->h.device));
+    return h->h.update_device(feasibility);
+}
+int asm_slp_extract_device(asm_slp *h) {
+    if (!h) return fail(ASM_E_INVALID, "null handle");
+    ASM_CK(cudaSetDevice(h->h.device));
+    return h->h.extract_device();
+}
+int asm_slp_timer_start(asm_slp *h) {
+    if (!h) return fail(ASM_E_INVALID, "null handle");
+    ASM_CK(cudaSetDevice(h->h.device));
+    if (!h->h.tev0) {
+        ASM_CK(cudaEventCreate(&h->h.tev0));
+        ASM_CK(cudaEventCreate(&h->h.tev1));
+    }
+    ASM_CK(cudaEventRecord(h->h.tev0, h->h.stream));
+    return ASM_OK;
+}
+int asm_slp_timer_stop(asm_slp *h, double *ms) {
+    if (!h || !ms) return fail(ASM_E_INVALID, "null argument");
+    if (!h->h.tev0) return fail(ASM_E_STATE, "timer not started");
+    ASM_CK(cudaSetDevice(h->h.device));
+    ASM_CK(cudaEventRecord(h->h.tev1, h->h.stream));
+    ASM_CK(cudaEventSynchronize(h->h.tev1));
+    float t = 0.f;
+    ASM_CK(cudaEventElapsedTime(&t, h->h.tev0, h->h.tev1));
+    *ms = t;
+    return ASM_OK;
+}
+int asm_slp_kernel_timing(asm_slp *h, int32_t reps, double *primal_ms, double *dual_ms) {
+    if (!h || reps < 1) return fail(ASM_E_INVALID, "bad argument");
+    if (!h->h.solved) return fail(ASM_E_STATE, "no solve yet");
+    ASM_CK(cudaSetDevice(h->h.device));
+    return h->h.cur()->time_streaming_kernels(reps, primal_ms, dual_ms);
 }
 
 }  // extern "C"

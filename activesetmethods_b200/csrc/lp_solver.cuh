@@ -17,6 +17,8 @@
 // A solve launches a CUDA graph of `check_every` iterations per host round trip; the only host<->device
 // traffic inside the loop is the 4-byte active counter.
 #pragma once
+#include <memory>
+
 #include "util.cuh"
 
 namespace asmb {
@@ -568,6 +570,10 @@ __global__ void __launch_bounds__(kThreads) k_finalize(LpView v) {
     }
 }
 
+}  // namespace asmb
+#include "pdhg_group.cuh"
+namespace asmb {
+
 // ================================================================================================================
 #define ASM_KL(...)      \
     do {                 \
@@ -600,7 +606,9 @@ class LpSolver {
     bool own_stream = false;
     // pattern
     DBuf<int> row_ptr, col_idx, col_ptr, row_idx, csc_src;
-    std::vector<int> h_row_ptr, h_col_idx;
+    std::vector<int> h_row_ptr, h_col_idx, h_col_ptr, h_row_idx, h_csc_src;
+    std::unique_ptr<GroupPlan> plan;  // persistent group engine (pdhg_group.cuh)
+    int last_engine = 0, last_G = 0, last_groups = 0;
     // data (unscaled, element-major)
     DBuf<double> vals, c, lb, ub, rl, ru, c0;
     DBuf<double> A, AT, dr, dc, sr, scf, cs, lbs, ubs, rls, rus;
@@ -648,7 +656,10 @@ class LpSolver {
         // host CSC + map CSC position -> CSR position
         h_row_ptr.resize(m + 1);
         h_col_idx.resize(nnz);
-        std::vector<int> cp(n + 1, 0), ri(nnz), src(nnz);
+        h_col_ptr.assign(n + 1, 0);
+        h_row_idx.resize(nnz);
+        h_csc_src.resize(nnz);
+        std::vector<int> &cp = h_col_ptr, &ri = h_row_idx, &src = h_csc_src;
         for (int i = 0; i <= m; ++i) {
             h_row_ptr[i] = (int)rp64[i];
             if (i && rp64[i] < rp64[i - 1]) return fail(ASM_E_INVALID, "row_ptr not monotone");
@@ -829,6 +840,239 @@ class LpSolver {
         return ASM_OK;
     }
 
+
+    // ---- persistent group engine -------------------------------------------------------------------------------
+    static constexpr size_t kSmemLimit = 227 * 1024 - 1024;  // dynamic shared memory available to one block
+
+    // sliced-ELL layout of the pattern for groups of G blocks; returns the dynamic shared memory a block needs
+    static size_t plan_layout(const LpSolver &L, int G, SellSide &R, SellSide &C, GroupSmem &sm) {
+        build_sell_side(L.m, L.h_row_ptr.data(), L.h_col_idx.data(), nullptr, G, R);
+        build_sell_side(L.n, L.h_col_ptr.data(), L.h_row_idx.data(), nullptr, G, C);
+        sm = GroupSmem();
+        for (int c = 0; c < G; ++c) {
+            sm.maxSellR = std::max(sm.maxSellR, R.ecnt[c]);
+            sm.maxSellC = std::max(sm.maxSellC, C.ecnt[c]);
+            sm.maxRpad = std::max(sm.maxRpad, R.nslice[c] * 32);
+            sm.maxCpad = std::max(sm.maxCpad, C.nslice[c] * 32);
+            sm.maxNSR = std::max(sm.maxNSR, R.nslice[c]);
+            sm.maxNSC = std::max(sm.maxNSC, C.nslice[c]);
+        }
+        // keep the double arrays 8-byte aligned
+        sm.maxSellR += sm.maxSellR & 1;
+        sm.maxSellC += sm.maxSellC & 1;
+        return sm.bytes();
+    }
+
+    // group size: the smallest that fits in shared memory; a single LP (or a batch smaller than the machine) takes
+    // more blocks so that a thread owns about one row and one column
+    int choose_group(int want, int n_sms) {
+        static const int cand[] = {1, 2, 4, 8, 16, 24, 32, 48, 64, 74, 96, 128, 148};
+        SellSide R, C;
+        GroupSmem sm;
+        if (want > 0) return plan_layout(*this, want, R, C, sm) <= kSmemLimit ? want : -1;
+        int fit = -1;
+        for (int g : cand) {
+            if (g > n_sms) break;
+            if (plan_layout(*this, g, R, C, sm) <= kSmemLimit) {
+                fit = g;
+                break;
+            }
+        }
+        if (fit < 0) return -1;
+        int G = fit;
+        for (int g : cand) {
+            if (g <= G || g > n_sms) continue;
+            if ((long long)Buser * g > n_sms) break;
+            if ((long long)std::max(n, m) > (long long)G * kGThreads || Buser * G * 2 <= n_sms) G = g;
+        }
+        return G;
+    }
+
+    int ensure_plan(int want_G) {
+        int dev = 0, n_sms = kSMs;
+        ASM_CK(cudaGetDevice(&dev));
+        ASM_CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        if (plan && (want_G <= 0 || plan->G == want_G)) return ASM_OK;
+        const int G = choose_group(want_G, n_sms);
+        if (G < 0) return fail(ASM_E_INVALID, "LP does not fit the shared memory of the machine (group engine)");
+        std::unique_ptr<GroupPlan> pl(new GroupPlan());
+        pl->G = G;
+        pl->cluster = G <= kMaxClusterG;
+        SellSide R, C;
+        plan_layout(*this, G, R, C, pl->sm);
+        // the value source of the column side is the CSC position itself (AT is stored in CSC order)
+        pl->cta.resize(G);
+        for (int c = 0; c < G; ++c) {
+            GroupCta &d = pl->cta[c];
+            d.r0 = R.first[c];
+            d.nR = R.cnt[c];
+            d.nSR = R.nslice[c];
+            d.sellR_base = R.base[c];
+            d.sellR_cnt = R.ecnt[c];
+            d.ptrR_base = R.ptr_base[c];
+            d.slotR_base = R.slot_base[c];
+            d.c0 = C.first[c];
+            d.nC = C.cnt[c];
+            d.nSC = C.nslice[c];
+            d.sellC_base = C.base[c];
+            d.sellC_cnt = C.ecnt[c];
+            d.ptrC_base = C.ptr_base[c];
+            d.slotC_base = C.slot_base[c];
+        }
+        auto up = [&](DBuf<int> &b, const std::vector<int> &h) -> int {
+            ASM_TRY(b.alloc(std::max<size_t>(h.size(), 1)));
+            if (!h.empty()) ASM_CK(cudaMemcpy(b.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+            return ASM_OK;
+        };
+        ASM_TRY(up(pl->sellR_src, R.src));
+        ASM_TRY(up(pl->sellR_idx, R.idx));
+        ASM_TRY(up(pl->ptrR, R.ptr));
+        ASM_TRY(up(pl->slotR, R.slot));
+        ASM_TRY(up(pl->sellC_src, C.src));
+        ASM_TRY(up(pl->sellC_idx, C.idx));
+        ASM_TRY(up(pl->ptrC, C.ptr));
+        ASM_TRY(up(pl->slotC, C.slot));
+        ASM_TRY(pl->d_cta.alloc(G));
+        ASM_CK(cudaMemcpy(pl->d_cta.p, pl->cta.data(), sizeof(GroupCta) * G, cudaMemcpyHostToDevice));
+        // how many groups can be resident at once
+        const size_t smem = pl->sm.bytes();
+        int groups = 1;
+        if (pl->cluster) {
+            ASM_CK(cudaFuncSetAttribute(k_pdhg_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (G > 8) ASM_CK(cudaFuncSetAttribute(k_pdhg_group<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(kGThreads);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = G;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int nc = 0;
+            ASM_CK(cudaOccupancyMaxActiveClusters(&nc, k_pdhg_group<true>, &cfg));
+            if (nc < 1) return fail(ASM_E_CUDA, "a cluster of this size cannot be scheduled");
+            groups = nc;
+        } else {
+            ASM_CK(cudaFuncSetAttribute(k_pdhg_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            ASM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pdhg_group<false>, kGThreads, smem));
+            if (per_sm < 1) return fail(ASM_E_CUDA, "group kernel does not fit on an SM");
+            groups = (n_sms * per_sm) / G;
+            if (groups < 1) return fail(ASM_E_CUDA, "group larger than the machine");
+        }
+        groups = std::min(groups, Buser);
+        pl->n_groups = groups;
+        const size_t gn = (size_t)groups * n, gm = (size_t)groups * std::max(m, 1);
+        DBuf<double> *cn[] = {&pl->gx, &pl->gx2, &pl->gxp, &pl->grc};
+        for (auto *b : cn) {
+            ASM_TRY(b->alloc(gn));
+            ASM_TRY(b->zero(stream));
+        }
+        DBuf<double> *rm[] = {&pl->gy, &pl->gyp, &pl->gray};
+        for (auto *b : rm) {
+            ASM_TRY(b->alloc(gm));
+            ASM_TRY(b->zero(stream));
+        }
+        ASM_TRY(pl->part.alloc((size_t)groups * G * Q_COUNT));
+        ASM_TRY(pl->bar.alloc(groups));
+        ASM_TRY(pl->queue.alloc(1));
+        ASM_TRY(pl->slot.alloc(groups));
+        plan = std::move(pl);
+        return ASM_OK;
+    }
+
+    int run_group(const asm_lp_params &P, int steps) {
+        GroupPlan &pl = *plan;
+        GroupArgs a;
+        a.v = view();
+        a.cta = pl.d_cta.p;
+        a.sellR_src = pl.sellR_src.p;
+        a.sellR_idx = pl.sellR_idx.p;
+        a.ptrR = pl.ptrR.p;
+        a.slotR = pl.slotR.p;
+        a.sellC_src = pl.sellC_src.p;
+        a.sellC_idx = pl.sellC_idx.p;
+        a.ptrC = pl.ptrC.p;
+        a.slotC = pl.slotC.p;
+        a.gx = pl.gx.p;
+        a.gx2 = pl.gx2.p;
+        a.gxp = pl.gxp.p;
+        a.grc = pl.grc.p;
+        a.gy = pl.gy.p;
+        a.gyp = pl.gyp.p;
+        a.gray = pl.gray.p;
+        a.part = pl.part.p;
+        a.bar = pl.bar.p;
+        a.queue = pl.queue.p;
+        a.slot = pl.slot.p;
+        a.G = pl.G;
+        a.Buser = Buser;
+        a.max_iter = P.max_iter;
+        a.steps = steps;
+        a.sm = pl.sm;
+        ASM_TRY(pl.bar.zero(stream));
+        ASM_TRY(pl.queue.zero(stream));
+        const size_t smem = pl.sm.bytes();
+        const unsigned grid = (unsigned)(pl.n_groups * pl.G);
+        if (pl.cluster) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(kGThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = pl.G;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            ASM_CK(cudaLaunchKernelEx(&cfg, k_pdhg_group<true>, a));
+        } else {
+            void *args[] = {(void *)&a};
+            ASM_CK(cudaLaunchCooperativeKernel((void *)k_pdhg_group<false>, dim3(grid), dim3(kGThreads), args, smem, stream));
+        }
+        ++launches;
+        last_G = pl.G;
+        last_groups = pl.n_groups;
+        return ASM_OK;
+    }
+
+    // average device time of one launch of each streaming kernel; scenarios are re-activated for the measurement
+    int time_streaming_kernels(int reps, double *primal_ms, double *dual_ms) {
+        LpView v = view();
+        const Geo gr = geo_for(m, B), gc = geo_for(n, B);
+        std::vector<ScenState> keep(B), live(B);
+        ASM_CK(cudaMemcpyAsync(keep.data(), state.p, sizeof(ScenState) * B, cudaMemcpyDeviceToHost, stream));
+        ASM_CK(cudaStreamSynchronize(stream));
+        live = keep;
+        for (auto &s : live) s.status = -1;
+        ASM_CK(cudaMemcpyAsync(state.p, live.data(), sizeof(ScenState) * B, cudaMemcpyHostToDevice, stream));
+        float t = 0.f;
+        for (int w = 0; w < 3; ++w) {
+            ASM_KB2(k_primal, false, gc, v, 1);
+            ASM_KB2(k_dual, false, gr, v, 1);
+        }
+        ASM_CK(cudaEventRecord(ev0, stream));
+        for (int r = 0; r < reps; ++r) ASM_KB2(k_primal, false, gc, v, 1);
+        ASM_CK(cudaEventRecord(ev1, stream));
+        ASM_CK(cudaEventSynchronize(ev1));
+        ASM_CK(cudaEventElapsedTime(&t, ev0, ev1));
+        if (primal_ms) *primal_ms = t / reps;
+        ASM_CK(cudaEventRecord(ev0, stream));
+        for (int r = 0; r < reps; ++r) ASM_KB2(k_dual, false, gr, v, 1);
+        ASM_CK(cudaEventRecord(ev1, stream));
+        ASM_CK(cudaEventSynchronize(ev1));
+        ASM_CK(cudaEventElapsedTime(&t, ev0, ev1));
+        if (dual_ms) *dual_ms = t / reps;
+        ASM_CK(cudaMemcpyAsync(state.p, keep.data(), sizeof(ScenState) * B, cudaMemcpyHostToDevice, stream));
+        ASM_CK(cudaStreamSynchronize(stream));
+        return ASM_OK;
+    }
+
     int solve(const asm_lp_params &P, asm_lp_info *info) {
         DevParams dp;
         dp.eps_rel = P.eps_rel;
@@ -852,18 +1096,33 @@ class LpSolver {
         ASM_CK(cudaMemcpyAsync(n_active.p, flag, sizeof(int), cudaMemcpyHostToDevice, stream));
         ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && has_solution) ? 1 : 0));
         const int steps = std::max(2, (int)P.check_every);
-        ASM_TRY(build_graph(steps));
-        ASM_CK(cudaEventRecord(ev0, stream));
-        int64_t it = 0;
-        while (it < P.max_iter) {
-            ASM_CK(cudaGraphLaunch(graph_exec, stream));
-            launches += launches_per_graph;
-            it += steps;
-            ASM_CK(cudaMemcpyAsync(flag, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-            ASM_CK(cudaStreamSynchronize(stream));
-            if (*flag <= 0) break;
+        // engine: 1 = one launch per half iteration (batch-streaming through HBM, CUDA graph per check period),
+        //         2 = persistent on-chip group kernel, 0 = group kernel when the LP fits, else streaming
+        bool group = P.engine == 2;
+        if (P.engine == 0) group = Buser == 1 && ensure_plan(P.group_size) == ASM_OK;
+        if (group) {
+            ASM_TRY(ensure_plan(P.group_size));
+            ASM_CK(cudaEventRecord(ev0, stream));
+            ASM_TRY(run_group(P, steps));
+            ASM_CK(cudaEventRecord(ev1, stream));
+            last_engine = 2;
+        } else {
+            ASM_TRY(build_graph(steps));
+            ASM_CK(cudaEventRecord(ev0, stream));
+            int64_t it = 0;
+            while (it < P.max_iter) {
+                ASM_CK(cudaGraphLaunch(graph_exec, stream));
+                launches += launches_per_graph;
+                it += steps;
+                ASM_CK(cudaMemcpyAsync(flag, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                ASM_CK(cudaStreamSynchronize(stream));
+                if (*flag <= 0) break;
+            }
+            ASM_CK(cudaEventRecord(ev1, stream));
+            last_engine = 1;
+            last_G = 0;
+            last_groups = 0;
         }
-        ASM_CK(cudaEventRecord(ev1, stream));
         LpView v = view();
         const Geo gm = geo_for(std::max(n, m), B);
         ASM_KB(k_finalize, gm, v);

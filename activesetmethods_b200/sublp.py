@@ -202,6 +202,35 @@ class SubLp:
                                                       1 if feasibility else 0, capi.dptr(out)))
         return self._ret(out)
 
+    # -- device-resident variants (inputs of the last ``update`` stay in HBM) -----------------------------------
+    def reassemble(self, feasibility=False):
+        capi.check(self._lib.asm_slp_reassemble(self._h, 1 if feasibility else 0))
+
+    def extract_device(self):
+        capi.check(self._lib.asm_slp_extract_device(self._h))
+
+    def timer_start(self):
+        capi.check(self._lib.asm_slp_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        capi.check(self._lib.asm_slp_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def kernel_timing(self, reps=50):
+        """Average device ms of one launch of (A'y + primal update, A xbar + dual update)."""
+        a = C.c_double()
+        b = C.c_double()
+        capi.check(self._lib.asm_slp_kernel_timing(self._h, int(reps), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def engine_info(self):
+        e = C.c_int32()
+        g = C.c_int32()
+        k = C.c_int32()
+        capi.check(self._lib.asm_slp_engine_info(self._h, C.byref(e), C.byref(g), C.byref(k)))
+        return dict(engine=e.value, group_size=g.value, groups=k.value)
+
     # -- instrumentation ----------------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self._lib.asm_slp_launch_count(self._h))

@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the SLP sub-LP hot path (BASELINE.json: "scenarios/s batched", config 5: load-perturbed
+case1354pegase scenarios split across the GPUs).
+
+A *step* is one pass of the per-iteration hot path of the reference
+(``sub_optimize!`` src/algorithms/subproblem.jl:229-542 + the merit reductions of src/algorithms/slp.jl:79-147)
+over one batch of scenarios: Jacobian assembly + sub-LP bounds, the LP solve to ``--eps`` (1e-6, the parity bar),
+the multiplier read-back with the reference's masking, the violation norm and the merit derivative.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle's HiGHS simplex on all host cores
+
+Per-GPU work is fixed (``--scenarios`` per GPU, default 128 so that N = 8 is the 1024-scenario config):
+weak scaling.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sub-LP scenarios/s (SLP hot path: assembly + bounds + LP solve to 1e-6 + read-back + merit)"
+UNIT = "scenarios/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--case", default="case1354pegase")
+    ap.add_argument("--scenarios", type=int, default=128, help="scenarios per GPU")
+    ap.add_argument("--eps", type=float, default=1e-6)
+    ap.add_argument("--delta", type=float, default=1000.0, help="step bound (Line Search uses 1000, slp.jl:23)")
+    ap.add_argument("--engine", type=int, default=0)
+    ap.add_argument("--max-iter", type=int, default=4_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=2, help="scenarios of the cpu_baseline sample")
+    ap.add_argument("--ref-sample", type=int, default=0, help="scenarios per reference step (0 = one per core)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# workload: first SLP linearisation (midpoint start, examples/acopf/init_opf.jl:25-29) of load scenarios
+# ------------------------------------------------------------------------------------------------------------
+def network(case):
+    from activesetmethods_b200.examples import acopf
+    if case == "case9":
+        return acopf.case9()
+    return acopf.synthetic_network(*acopf.PEGASE_SHAPES[case])
+
+
+def linearise(net, scenario_ids):
+    """Host NLP evaluation (the JuMP evaluator's role, MOI_wrapper.jl:1047-1069) of every scenario at x0."""
+    from activesetmethods_b200.examples import acopf
+    out = dict(x=[], f=[], df=[], E=[], dE=[], gL=[], gU=[], xL=[], xU=[])
+    mdl0 = None
+    for sid in scenario_ids:
+        mdl = acopf.AcopfModel(acopf.perturb_loads(net, sid))
+        mdl0 = mdl0 or mdl
+        x = np.clip(mdl.x0, mdl.x_L, mdl.x_U)
+        out["x"].append(x)
+        out["f"].append(mdl.eval_f(x))
+        out["df"].append(mdl.eval_grad_f(x, np.zeros(mdl.n)))
+        out["E"].append(mdl.eval_g(x, np.zeros(mdl.m)))
+        out["dE"].append(mdl.eval_jac_g(x, "eval", None, None, np.zeros(mdl.nnz)))
+        out["gL"].append(mdl.g_L)
+        out["gU"].append(mdl.g_U)
+        out["xL"].append(mdl.x_L)
+        out["xU"].append(mdl.x_U)
+    return mdl0, {k: np.ascontiguousarray(np.array(v, dtype=np.float64)) for k, v in out.items()}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle: restated sub-LP build + HiGHS dual simplex) -- the checker used as the reported baseline
+# ------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(case):
+    from oracle import slp_oracle as so
+    net = network(case)
+    _W["net"], _W["so"] = net, so
+
+
+def _cpu_solve(args):
+    sid, delta = args
+    so = _W["so"]
+    mdl, d = linearise(_W["net"], [sid])
+    pat = so.JacobianPattern(mdl.m, mdl.n, mdl.j_str)
+    ref = so.SubLp(pat, d["gL"][0], d["gU"][0], d["xL"][0], d["xU"][0])
+    t0 = time.perf_counter()
+    out = ref.solve(pat.assemble(d["dE"][0]), d["df"][0], d["f"][0], d["E"][0], d["x"][0], delta, False)
+    return time.perf_counter() - t0, int(out[5]), ref.last_objective
+
+
+def cpu_baseline(case, delta, n_scen):
+    _cpu_init(case)
+    t0 = time.perf_counter()
+    res = [_cpu_solve((1 + s, delta)) for s in range(n_scen)]
+    dt = time.perf_counter() - t0
+    solve_t = sum(r[0] for r in res)
+    return {"value": n_scen / solve_t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_scen} scenarios of {case} (first SLP linearisation), oracle sub-LP build + HiGHS dual "
+                      f"simplex, 1 thread, {solve_t:.1f} s of solve time ({dt:.1f} s wall incl. host NLP evaluation)",
+            "objectives": [r[2] for r in res]}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = a.ref_sample or cores
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(a.case,)) as pool:
+        def step(k):
+            ids = [(1 + k * per_step + s, a.delta) for s in range(per_step)]
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_solve, ids, chunksize=1)
+            return time.perf_counter() - t0, res
+        for k in range(a.warmup):
+            step(k)
+        t_total, n_ok = 0.0, 0
+        for k in range(a.steps):
+            dt, res = step(a.warmup + k)
+            t_total += dt
+            n_ok += sum(1 for r in res if r[1] == 0)
+    value = per_step * a.steps / t_total
+    sample = (f"{per_step} scenarios of {a.case} per step over a {cores}-process pool (one HiGHS dual simplex per "
+              f"core), host NLP evaluation included in the step")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * t_total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{a.case} load scenarios, first SLP linearisation, sub-LP to simplex tolerance 1e-9",
+                   "scenarios_per_step": per_step, "delta": a.delta, "optimal": n_ok},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        g.build()
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from activesetmethods_b200 import capi
+    from activesetmethods_b200.sublp import SubLp
+    lib = capi.load()
+    if lib.asm_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+
+    S = a.scenarios
+    net = network(a.case)
+    ids = [1 + rank * S + s for s in range(S)]          # scenario id = seed
+    mdl, d = linearise(net, ids)
+    n, m, nnz = mdl.n, mdl.m, mdl.nnz
+    lp = SubLp(n, m, mdl.j_str, d["xL"], d["xU"], d["gL"], d["gU"], batch=S, device=local, eps_rel=a.eps,
+               engine=a.engine, max_iter=a.max_iter)
+    nnz_csr = lp.nnz_csr
+
+    def pinned(shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+
+    hin = {k: pinned(d[k].shape) for k in ("x", "f", "df", "E", "dE")}
+    for k in hin:
+        hin[k][...] = d[k]
+    hdelta = pinned((S,))
+    hdelta[...] = a.delta
+    hout = dict(p=pinned((S, n)), lam=pinned((S, m)), mu_u=pinned((S, n)), mu_l=pinned((S, n)),
+                slack=pinned((S, m, 2)), viol=pinned((S,)), deriv=pinned((S,)))
+    hstatus = torch.empty(S, dtype=torch.int32).pin_memory().numpy()
+    info = (capi.LpInfo * S)()
+    P = capi.dptr
+
+    def e2e_step():
+        """What a caller of the plugin does per SLP iteration: host buffers in, host results out."""
+        capi.check(lib.asm_slp_sub_optimize(
+            lp._h, P(hin["x"]), P(hin["f"]), P(hin["df"]), P(hin["E"]), P(hin["dE"]), P(hdelta), 0,
+            C.byref(lp.params), P(hout["p"]), P(hout["lam"]), P(hout["mu_u"]), P(hout["mu_l"]), P(hout["slack"]),
+            hstatus.ctypes.data_as(capi.c_int32_p), info))
+        capi.check(lib.asm_slp_norm_violations(lp._h, None, None, 0, P(hout["viol"])))
+        nu = np.abs(hout["lam"])                              # compute_nu!, slp_line_search.jl:251-261
+        capi.check(lib.asm_slp_merit_derivative(lp._h, P(nu), 0, P(hout["deriv"])))
+
+    def resident_step():
+        """Same work with x_k, df, E, dE already in HBM: device time from CUDA events on the handle's stream."""
+        lp.timer_start()
+        lp.reassemble(False)
+        capi.check(lib.asm_slp_solve(lp._h, C.byref(lp.params), info))
+        lp.extract_device()
+        capi.check(lib.asm_slp_norm_violations(lp._h, None, None, 0, P(hout["viol"])))
+        return lp.timer_stop()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    lp.update(hin["x"], hin["f"], hin["df"], hin["E"], hin["dE"], hdelta, False)   # inputs resident
+    for _ in range(a.warmup):
+        resident_step()
+    clocks = ClockSampler(local)
+    sync_all()
+    clocks.start()
+    l0 = lp.launch_count()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(a.steps):
+        dev_ms += resident_step()
+    sync_all()
+    wall_resident = time.perf_counter() - t0
+    launches = lp.launch_count() - l0
+    infos = [dict(status=int(i.status), iterations=int(i.iterations), objective=float(i.objective)) for i in info[:S]]
+    loop_ms, loop_its = lp.last_solve_timing()
+    eng = lp.engine_info()
+    dev_s = max_over_ranks(dev_ms * 1e-3)
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        e2e_step()
+    sync_all()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop()
+    n_opt = sum_over_ranks(float(sum(1 for i in infos if i["status"] == 0)))
+    its_max = max_over_ranks(float(max(i["iterations"] for i in infos)))
+    its_sum = sum_over_ranks(float(sum(i["iterations"] for i in infos)))
+    total_scen = S * world
+    value = total_scen * a.steps / dev_s
+    e2e = total_scen * a.steps / e2e_s
+    h2d = 8 * S * (2 * n + m + nnz + 2) + 8 * S * m          # sub_optimize inputs + nu
+    d2h = 8 * S * (3 * n + m + 2 * m) + 4 * S + 8 * S * 2    # p, lambda, mu_U, mu_L, slacks, status, 2 merit scalars
+
+    # ---- roofline of the dominant kernels: the streaming PDHG iteration pair, measured live
+    pm, dm = lp.kernel_timing(50)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    Bp = lp.params  # noqa: F841
+    Bpad = ((S + 31) // 32) * 32 if S > 1 else 1
+    by_primal = Bpad * (8 * nnz_csr + 8 * m + 56 * n) + 4 * nnz_csr + 4 * (n + 1)
+    by_dual = Bpad * (8 * nnz_csr + 8 * n + 40 * m) + 4 * nnz_csr + 4 * (m + 1)
+    achieved = (by_primal + by_dual) / ((pm + dm) * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"{a.case}:{S}")
+        except (OSError, ValueError):
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+                "kernel": "k_primal<batch> + k_dual<batch> (one PDHG iteration of the whole batch)",
+                "bytes_per_launch_pair": by_primal + by_dual, "primal_ms": pm, "dual_ms": dm,
+                "primal_gbs": by_primal / (pm * 1e-3) / 1e9, "dual_gbs": by_dual / (dm * 1e-3) / 1e9,
+                "loop_ms_per_iteration": loop_ms / max(loop_its, 1)}
+
+    cpu = None
+    if rank == 0 and world == 1 and a.cpu_sample > 0:
+        cpu = cpu_baseline(a.case, a.delta, a.cpu_sample)
+        # the same scenarios on the GPU must agree with the checker (objective to 1e-6 relative)
+        for s, obj in enumerate(cpu.pop("objectives")):
+            if obj is not None and infos[s]["status"] == 0:
+                rel = abs(infos[s]["objective"] - obj) / max(1.0, abs(obj))
+                if rel > 1e-6:
+                    raise RuntimeError(f"scenario {s}: GPU objective {infos[s]['objective']} vs oracle {obj} (rel {rel:.2e})")
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{S} load-perturbed {a.case} scenarios per GPU ({total_scen} total; 8 GPUs = the "
+                                   f"1024-scenario config), first SLP linearisation, Line Search step bound {a.delta:g}",
+                       "n": n, "m": m, "nnz_coo": nnz, "nnz_csr": nnz_csr, "eps_rel": a.eps,
+                       "engine": eng, "optimal": int(n_opt), "pdhg_iterations_max": int(its_max),
+                       "pdhg_iterations_mean": its_sum / total_scen,
+                       "l2": "no flush: the batch working set (%.0f MB) exceeds the 126 MB L2" %
+                             (Bpad * (16 * nnz_csr + 64 * n + 48 * m) / 1e6),
+                       "wall_s_resident": wall_resident},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clk,
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    lp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,7 +64,10 @@ typedef struct asm_lp_params {
     double restart_necessary;  /* 0.8  */
     double restart_artificial; /* 0.36 */
     double pid_kp, pid_ki, pid_kd; /* primal-weight controller on log(w |dx|/|dy|); (0.5, 0, 0) = PDLP rule  */
-    double reserved[4];
+    int32_t engine;        /* 0 auto; 1 streaming kernels (one launch per half iteration, CUDA graph);       */
+                           /* 2 persistent group kernel (LP resident in the shared memory of G blocks)       */
+    int32_t group_size;    /* blocks per LP for engine 2 (0 = auto)                                          */
+    double reserved[3];
 } asm_lp_params;
 void asm_lp_default_params(asm_lp_params *p);
 
@@ -182,6 +185,24 @@ int64_t asm_slp_launch_count(asm_slp *h);
 /* device time (ms, CUDA events on the handle's stream) of the PDHG loop of the last asm_slp_solve and
  * the total PDHG iterations it ran (max over the batch) */
 int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations);
+
+/* which engine the last asm_slp_solve used (1 streaming, 2 group), blocks per LP and LPs resident at once */
+int asm_slp_engine_info(asm_slp *h, int32_t *engine, int32_t *group_size, int32_t *groups);
+
+/* ---- device-resident variants (bench.py's `value`: inputs already in HBM) ----------------------------- */
+/* the device part of asm_slp_update (assembly + bounds, subproblem.jl:248-484) on the x_k, df, E, dE, delta
+ * already resident from the last asm_slp_update */
+int asm_slp_reassemble(asm_slp *h, int32_t feasibility);
+/* the device part of asm_slp_extract (masking / range-row sums of subproblem.jl:500-536), no copy to the host */
+int asm_slp_extract_device(asm_slp *h);
+/* CUDA-event timer on the handle's own stream: start records an event, stop records another, waits for it
+ * and returns the elapsed device time */
+int asm_slp_timer_start(asm_slp *h);
+int asm_slp_timer_stop(asm_slp *h, double *ms);
+/* average duration (ms) of one launch of the two streaming PDHG kernels (A'y + primal update, A xbar + dual
+ * update) over `reps` back-to-back launches each, CUDA events on the handle's stream.  Needs a solved LP;
+ * the iterate is advanced (benchmark use only) */
+int asm_slp_kernel_timing(asm_slp *h, int32_t reps, double *primal_ms, double *dual_ms);
 
 #ifdef __cplusplus
 }
