@@ -17,6 +17,7 @@
 // A solve launches a CUDA graph of `check_every` iterations per host round trip; the only host<->device
 // traffic inside the loop is the 4-byte active counter.
 #pragma once
+#include <map>
 #include <memory>
 
 #include "util.cuh"
@@ -607,7 +608,9 @@ class LpSolver {
     // pattern
     DBuf<int> row_ptr, col_idx, col_ptr, row_idx, csc_src;
     std::vector<int> h_row_ptr, h_col_idx, h_col_ptr, h_row_idx, h_csc_src;
-    std::unique_ptr<GroupPlan> plan;  // persistent group engine (pdhg_group.cuh)
+    std::map<int, std::unique_ptr<GroupPlan>> plans;  // persistent group engine (pdhg_group.cuh), by group size
+    std::map<int, std::pair<size_t, int>> feas;       // group size -> (shared memory bytes, matrix resident)
+    GroupPlan *plan = nullptr;
     int last_engine = 0, last_G = 0, last_groups = 0;
     // data (unscaled, element-major)
     DBuf<double> vals, c, lb, ub, rl, ru, c0;
@@ -842,12 +845,13 @@ class LpSolver {
 
 
     // ---- persistent group engine -------------------------------------------------------------------------------
-    static constexpr size_t kSmemLimit = 227 * 1024 - 1024;  // dynamic shared memory available to one block
+    static constexpr size_t kSmemLimit = 227 * 1024 - 4096;  // dynamic shared memory available to one block
 
     // sliced-ELL layout of the pattern for groups of G blocks; returns the dynamic shared memory a block needs
+    // (matrix values kept in shared memory when they fit, else streamed from L2), or 0 when G is infeasible
     static size_t plan_layout(const LpSolver &L, int G, SellSide &R, SellSide &C, GroupSmem &sm) {
-        build_sell_side(L.m, L.h_row_ptr.data(), L.h_col_idx.data(), nullptr, G, R);
-        build_sell_side(L.n, L.h_col_ptr.data(), L.h_row_idx.data(), nullptr, G, C);
+        build_sell_side(L.m, L.n, L.h_row_ptr.data(), L.h_col_idx.data(), nullptr, G, R);
+        build_sell_side(L.n, L.m, L.h_col_ptr.data(), L.h_row_idx.data(), nullptr, G, C);
         sm = GroupSmem();
         for (int c = 0; c < G; ++c) {
             sm.maxSellR = std::max(sm.maxSellR, R.ecnt[c]);
@@ -856,45 +860,80 @@ class LpSolver {
             sm.maxCpad = std::max(sm.maxCpad, C.nslice[c] * 32);
             sm.maxNSR = std::max(sm.maxNSR, R.nslice[c]);
             sm.maxNSC = std::max(sm.maxNSC, C.nslice[c]);
+            sm.maxHaloR = std::max(sm.maxHaloR, R.halo_cnt[c]);
+            sm.maxHaloC = std::max(sm.maxHaloC, C.halo_cnt[c]);
         }
-        // keep the double arrays 8-byte aligned
-        sm.maxSellR += sm.maxSellR & 1;
-        sm.maxSellC += sm.maxSellC & 1;
+        if (sm.maxHaloR > 65535 || sm.maxHaloC > 65535) return 0;  // halo positions are 16-bit
+        // keep every carved array 8-byte aligned
+        sm.maxSellR = (sm.maxSellR + 3) & ~3;
+        sm.maxSellC = (sm.maxSellC + 3) & ~3;
+        sm.maxHaloR = (sm.maxHaloR + 1) & ~1;
+        sm.maxHaloC = (sm.maxHaloC + 1) & ~1;
+        sm.maxNSR |= 1;   // (maxNSR + 1) + (maxNSC + 1) ints: keep the 16-bit arrays 8-byte aligned
+        sm.maxNSC |= 1;
+        sm.mats = 1;
+        if (sm.bytes() > kSmemLimit) sm.mats = 0;
         return sm.bytes();
     }
+    static bool plan_fits(size_t bytes) { return bytes > 0 && bytes <= kSmemLimit; }
 
-    // group size: the smallest that fits in shared memory; a single LP (or a batch smaller than the machine) takes
-    // more blocks so that a thread owns about one row and one column
-    int choose_group(int want, int n_sms) {
-        static const int cand[] = {1, 2, 4, 8, 16, 24, 32, 48, 64, 74, 96, 128, 148};
+    const std::pair<size_t, int> &feasible(int G) {
+        auto it = feas.find(G);
+        if (it != feas.end()) return it->second;
         SellSide R, C;
         GroupSmem sm;
-        if (want > 0) return plan_layout(*this, want, R, C, sm) <= kSmemLimit ? want : -1;
-        int fit = -1;
+        const size_t b = plan_layout(*this, G, R, C, sm);
+        return feas[G] = std::make_pair(plan_fits(b) ? b : (size_t)0, sm.mats);
+    }
+
+    // Blocks per LP for `live` LPs that want to run at once.  Cost model from measurements on B200 (profiles/):
+    // one iteration takes ~2.8 us of synchronisation in a cluster (4.4 us across clusters) plus ~1.5 ns per
+    // matrix entry divided by the blocks.  Many LPs: the smallest group that keeps the matrix in shared memory
+    // (throughput); few LPs: widen until the machine is used (latency).
+    int choose_group(int want, int live, int n_sms) {
+        static const int cand[] = {1, 2, 4, 8, 16, 24, 32, 48, 64, 74, 96, 128, 148};
+        if (want > 0) return feasible(want).first ? want : -1;
+        int base = -1;
         for (int g : cand) {
             if (g > n_sms) break;
-            if (plan_layout(*this, g, R, C, sm) <= kSmemLimit) {
-                fit = g;
+            const auto &f = feasible(g);
+            if (!f.first) continue;
+            if (base < 0) base = g;
+            if (f.second) {                       // matrix resident: take it unless it needs the slow barrier
+                if (g <= kMaxClusterG || base > kMaxClusterG) base = g;
                 break;
             }
+            if (g >= kMaxClusterG && base <= kMaxClusterG) break;
         }
-        if (fit < 0) return -1;
-        int G = fit;
+        if (base < 0) return -1;
+        const double work = 1.5e-3 * (double)nnz;
+        auto cost = [&](int g) { return (g <= kMaxClusterG ? 2.8 : 4.4) + work / g; };
+        int G = base;
         for (int g : cand) {
-            if (g <= G || g > n_sms) continue;
-            if ((long long)Buser * g > n_sms) break;
-            if ((long long)std::max(n, m) > (long long)G * kGThreads || Buser * G * 2 <= n_sms) G = g;
+            if (g <= base || g > n_sms) continue;
+            if ((long long)live * g > n_sms) break;
+            if (!feasible(g).first) continue;
+            if (cost(g) < 0.92 * cost(G)) G = g;
         }
         return G;
     }
 
-    int ensure_plan(int want_G) {
+    static const void *group_kernel(bool cluster, bool mats) {
+        if (cluster) return mats ? (const void *)k_pdhg_group<true, true> : (const void *)k_pdhg_group<true, false>;
+        return mats ? (const void *)k_pdhg_group<false, true> : (const void *)k_pdhg_group<false, false>;
+    }
+
+    int ensure_plan(int want_G, int live) {
         int dev = 0, n_sms = kSMs;
         ASM_CK(cudaGetDevice(&dev));
         ASM_CK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-        if (plan && (want_G <= 0 || plan->G == want_G)) return ASM_OK;
-        const int G = choose_group(want_G, n_sms);
+        const int G = choose_group(want_G, std::max(1, live), n_sms);
         if (G < 0) return fail(ASM_E_INVALID, "LP does not fit the shared memory of the machine (group engine)");
+        auto found = plans.find(G);
+        if (found != plans.end()) {
+            plan = found->second.get();
+            return ASM_OK;
+        }
         std::unique_ptr<GroupPlan> pl(new GroupPlan());
         pl->G = G;
         pl->cluster = G <= kMaxClusterG;
@@ -911,6 +950,8 @@ class LpSolver {
             d.sellR_cnt = R.ecnt[c];
             d.ptrR_base = R.ptr_base[c];
             d.slotR_base = R.slot_base[c];
+            d.haloR_base = R.halo_base[c];
+            d.haloR_cnt = R.halo_cnt[c];
             d.c0 = C.first[c];
             d.nC = C.cnt[c];
             d.nSC = C.nslice[c];
@@ -918,7 +959,11 @@ class LpSolver {
             d.sellC_cnt = C.ecnt[c];
             d.ptrC_base = C.ptr_base[c];
             d.slotC_base = C.slot_base[c];
+            d.haloC_base = C.halo_base[c];
+            d.haloC_cnt = C.halo_cnt[c];
         }
+        pl->totSellR = (int)R.src.size();
+        pl->totSellC = (int)C.src.size();
         auto up = [&](DBuf<int> &b, const std::vector<int> &h) -> int {
             ASM_TRY(b.alloc(std::max<size_t>(h.size(), 1)));
             if (!h.empty()) ASM_CK(cudaMemcpy(b.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -928,6 +973,12 @@ class LpSolver {
         ASM_TRY(up(pl->sellR_idx, R.idx));
         ASM_TRY(up(pl->ptrR, R.ptr));
         ASM_TRY(up(pl->slotR, R.slot));
+        ASM_TRY(up(pl->haloR, R.halo));
+        ASM_TRY(up(pl->haloC, C.halo));
+        ASM_TRY(pl->tailR.alloc(std::max<size_t>(R.tail.size(), 1)));
+        ASM_TRY(pl->tailC.alloc(std::max<size_t>(C.tail.size(), 1)));
+        if (!R.tail.empty()) ASM_CK(cudaMemcpy(pl->tailR.p, R.tail.data(), R.tail.size(), cudaMemcpyHostToDevice));
+        if (!C.tail.empty()) ASM_CK(cudaMemcpy(pl->tailC.p, C.tail.data(), C.tail.size(), cudaMemcpyHostToDevice));
         ASM_TRY(up(pl->sellC_src, C.src));
         ASM_TRY(up(pl->sellC_idx, C.idx));
         ASM_TRY(up(pl->ptrC, C.ptr));
@@ -937,9 +988,10 @@ class LpSolver {
         // how many groups can be resident at once
         const size_t smem = pl->sm.bytes();
         int groups = 1;
+        const void *fn = group_kernel(pl->cluster, pl->sm.mats != 0);
+        ASM_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (pl->cluster) {
-            ASM_CK(cudaFuncSetAttribute(k_pdhg_group<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            if (G > 8) ASM_CK(cudaFuncSetAttribute(k_pdhg_group<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            if (G > 8) ASM_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(G);
             cfg.blockDim = dim3(kGThreads);
@@ -952,19 +1004,19 @@ class LpSolver {
             cfg.attrs = at;
             cfg.numAttrs = 1;
             int nc = 0;
-            ASM_CK(cudaOccupancyMaxActiveClusters(&nc, k_pdhg_group<true>, &cfg));
+            ASM_CK(cudaOccupancyMaxActiveClusters(&nc, fn, &cfg));
             if (nc < 1) return fail(ASM_E_CUDA, "a cluster of this size cannot be scheduled");
             groups = nc;
         } else {
-            ASM_CK(cudaFuncSetAttribute(k_pdhg_group<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
-            ASM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pdhg_group<false>, kGThreads, smem));
+            ASM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kGThreads, smem));
             if (per_sm < 1) return fail(ASM_E_CUDA, "group kernel does not fit on an SM");
             groups = (n_sms * per_sm) / G;
             if (groups < 1) return fail(ASM_E_CUDA, "group larger than the machine");
         }
         groups = std::min(groups, Buser);
         pl->n_groups = groups;
+        pl->max_groups = groups;
         const size_t gn = (size_t)groups * n, gm = (size_t)groups * std::max(m, 1);
         DBuf<double> *cn[] = {&pl->gx, &pl->gx2, &pl->gxp, &pl->grc};
         for (auto *b : cn) {
@@ -976,16 +1028,23 @@ class LpSolver {
             ASM_TRY(b->alloc(gm));
             ASM_TRY(b->zero(stream));
         }
+        if (!pl->sm.mats) {
+            ASM_TRY(pl->gA.alloc((size_t)groups * pl->totSellR));
+            ASM_TRY(pl->gAT.alloc((size_t)groups * pl->totSellC));
+            ASM_TRY(pl->gconst.alloc((size_t)groups * G * (2 * (size_t)pl->sm.maxRpad + 3 * (size_t)pl->sm.maxCpad)));
+        }
         ASM_TRY(pl->part.alloc((size_t)groups * G * Q_COUNT));
         ASM_TRY(pl->bar.alloc(groups));
         ASM_TRY(pl->queue.alloc(1));
         ASM_TRY(pl->slot.alloc(groups));
-        plan = std::move(pl);
+        plan = pl.get();
+        plans[G] = std::move(pl);
         return ASM_OK;
     }
 
-    int run_group(const asm_lp_params &P, int steps) {
+    int run_group(const asm_lp_params &P, int steps, int live, long long budget) {
         GroupPlan &pl = *plan;
+        pl.n_groups = std::max(1, std::min(pl.max_groups, live));
         GroupArgs a;
         a.v = view();
         a.cta = pl.d_cta.p;
@@ -993,6 +1052,15 @@ class LpSolver {
         a.sellR_idx = pl.sellR_idx.p;
         a.ptrR = pl.ptrR.p;
         a.slotR = pl.slotR.p;
+        a.haloR = pl.haloR.p;
+        a.haloC = pl.haloC.p;
+        a.tailR = pl.tailR.p;
+        a.tailC = pl.tailC.p;
+        a.gA = pl.gA.p;
+        a.gAT = pl.gAT.p;
+        a.gconst = pl.gconst.p;
+        a.totSellR = pl.totSellR;
+        a.totSellC = pl.totSellC;
         a.sellC_src = pl.sellC_src.p;
         a.sellC_idx = pl.sellC_idx.p;
         a.ptrC = pl.ptrC.p;
@@ -1011,12 +1079,15 @@ class LpSolver {
         a.G = pl.G;
         a.Buser = Buser;
         a.max_iter = P.max_iter;
-        a.steps = steps;
+        a.budget = budget;
+        a.steps = std::min(steps, kMaxSteps);
         a.sm = pl.sm;
         ASM_TRY(pl.bar.zero(stream));
         ASM_TRY(pl.queue.zero(stream));
         const size_t smem = pl.sm.bytes();
         const unsigned grid = (unsigned)(pl.n_groups * pl.G);
+        const void *fn = group_kernel(pl.cluster, pl.sm.mats != 0);
+        void *args[] = {(void *)&a};
         if (pl.cluster) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
@@ -1030,10 +1101,9 @@ class LpSolver {
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            ASM_CK(cudaLaunchKernelEx(&cfg, k_pdhg_group<true>, a));
+            ASM_CK(cudaLaunchKernelExC(&cfg, fn, args));
         } else {
-            void *args[] = {(void *)&a};
-            ASM_CK(cudaLaunchCooperativeKernel((void *)k_pdhg_group<false>, dim3(grid), dim3(kGThreads), args, smem, stream));
+            ASM_CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kGThreads), args, smem, stream));
         }
         ++launches;
         last_G = pl.G;
@@ -1098,17 +1168,20 @@ class LpSolver {
         const int steps = std::max(2, (int)P.check_every);
         // engine: 1 = one launch per half iteration (batch-streaming through HBM, CUDA graph per check period),
         //         2 = persistent on-chip group kernel, 0 = group kernel when the LP fits, else streaming
-        bool group = P.engine == 2;
-        if (P.engine == 0) group = Buser == 1 && ensure_plan(P.group_size) == ASM_OK;
-        if (group) {
-            ASM_TRY(ensure_plan(P.group_size));
-            ASM_CK(cudaEventRecord(ev0, stream));
-            ASM_TRY(run_group(P, steps));
-            ASM_CK(cudaEventRecord(ev1, stream));
-            last_engine = 2;
-        } else {
+        // engine 0: a single LP runs on the group kernel; a batch streams until a quarter of it is left, then the
+        // stragglers finish on the group kernel, each to its own convergence
+        const int hand_over = Buser == 1 ? 0 : std::max(1, Buser / 4);
+        const bool plan_ok = P.engine != 1 && ensure_plan(P.group_size, P.engine == 2 ? Buser : std::max(1, hand_over)) == ASM_OK;
+        if (P.engine == 2 && !plan_ok) return ensure_plan(P.group_size, Buser);
+        const bool group_only = plan_ok && (P.engine == 2 || Buser == 1);
+        ASM_CK(cudaEventRecord(ev0, stream));
+        last_engine = 0;
+        last_G = 0;
+        last_groups = 0;
+        int live = Buser;
+        bool limit = false;
+        if (!group_only) {
             ASM_TRY(build_graph(steps));
-            ASM_CK(cudaEventRecord(ev0, stream));
             int64_t it = 0;
             while (it < P.max_iter) {
                 ASM_CK(cudaGraphLaunch(graph_exec, stream));
@@ -1116,13 +1189,25 @@ class LpSolver {
                 it += steps;
                 ASM_CK(cudaMemcpyAsync(flag, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
                 ASM_CK(cudaStreamSynchronize(stream));
-                if (*flag <= 0) break;
+                if (*flag <= (plan_ok ? hand_over : 0)) break;
             }
-            ASM_CK(cudaEventRecord(ev1, stream));
-            last_engine = 1;
-            last_G = 0;
-            last_groups = 0;
+            live = *flag;
+            limit = it >= P.max_iter;
+            last_engine |= 1;
         }
+        // group phase: re-planned as the live set thins out (wider groups for the last stragglers)
+        while (plan_ok && live > 0 && !limit) {
+            ASM_TRY(ensure_plan(P.group_size, live));
+            const long long budget = live > 1 ? (1LL << 16) : P.max_iter;
+            ASM_TRY(run_group(P, steps, live, budget));
+            last_engine |= 2;
+            ASM_CK(cudaMemcpyAsync(host_state.data(), state.p, sizeof(ScenState) * B, cudaMemcpyDeviceToHost, stream));
+            ASM_CK(cudaStreamSynchronize(stream));
+            live = 0;
+            for (int s = 0; s < Buser; ++s)
+                if (host_state[s].status < 0 && host_state[s].total < P.max_iter) ++live;
+        }
+        ASM_CK(cudaEventRecord(ev1, stream));
         LpView v = view();
         const Geo gm = geo_for(std::max(n, m), B);
         ASM_KB(k_finalize, gm, v);

@@ -5,10 +5,13 @@
 // subproblem.jl:490) needs 10^4..10^6 PDHG iterations of two dependent SpMVs each.  One LP is at most
 // ~37 MB per iteration, so a launch-per-half-iteration design is bound by launch latency
 // (~7 us per kernel) and not by HBM.  Here the scaled matrix K (sliced-ELL, rows sorted by length inside a
-// block) and K' live in the shared memory of the G blocks for the whole solve, the iterate pieces (x, y,
-// anchors, bounds) too; only the two exchange vectors (xbar, y) go through L2.  A block owns a contiguous
-// range of rows and of columns; a warp owns 32-slot slices.  Blocks of a group meet at two barriers per
-// iteration:
+// block) and K' live in the shared memory of the G blocks for the whole solve (MATS) or stream from L2 in
+// sliced-ELL order (large LPs), the iterate pieces (x, y, anchors, bounds) are always in shared memory; only the
+// two exchange vectors (xbar, y) go through L2: after each barrier a block copies the entries its rows (columns)
+// touch -- its *halo*, a sorted index list fixed by the pattern -- into shared memory with near-coalesced loads
+// and gathers from there (an SM sustains only ~0.5 scattered global loads per cycle, but ~8 shared ones).
+// A block owns a contiguous range of rows and of columns; a warp owns 32-slot slices.  Blocks of a group meet at
+// two barriers per iteration:
 //   CLUSTER mode  G <= 16 : the group is a thread-block cluster, barrier = barrier.cluster (hardware)
 //   GRID mode     G  > 16 : cooperative launch, barrier = one global counter per group
 // Groups pull LPs of the batch from an atomic queue, so every LP stops at its own convergence.
@@ -22,21 +25,28 @@ namespace asmb {
 constexpr int kGThreads = 1024;
 constexpr int kGWarps = kGThreads / 32;
 constexpr int kMaxClusterG = 16;
+constexpr int kMaxSteps = 256;  // check_every is capped to this in the group engine
 
 struct GroupCta {
-    int r0, nR, nSR, sellR_base, sellR_cnt, ptrR_base, slotR_base;
-    int c0, nC, nSC, sellC_base, sellC_cnt, ptrC_base, slotC_base;
+    int r0, nR, nSR, sellR_base, sellR_cnt, ptrR_base, slotR_base, haloR_base, haloR_cnt;
+    int c0, nC, nSC, sellC_base, sellC_cnt, ptrC_base, slotC_base, haloC_base, haloC_cnt;
 };
 
 // shared-memory carve (element counts are the maxima over the blocks of the group)
 struct GroupSmem {
-    int maxSellR, maxSellC, maxRpad, maxCpad, maxNSR, maxNSC;
+    int maxSellR, maxSellC, maxRpad, maxCpad, maxNSR, maxNSC, maxHaloR, maxHaloC;
+    int mats;  // 1: matrix values in shared memory, 0: streamed from L2
     size_t bytes() const {
         size_t b = 0;
-        b += sizeof(double) * ((size_t)maxSellR + maxSellC);
-        b += sizeof(double) * (4 * (size_t)maxRpad + 5 * (size_t)maxCpad);
+        if (mats) b += sizeof(double) * ((size_t)maxSellR + maxSellC);
+        // iterates (y, anchor | x, anchor) always; the per-slot constants (rl, ru | c, lb, ub) only next to the
+        // matrix values -- in streaming mode they are re-read from L2 together with the halo
+        b += sizeof(double) * ((mats ? 4 : 2) * (size_t)maxRpad + (mats ? 5 : 2) * (size_t)maxCpad);
+        b += sizeof(double) * ((size_t)maxHaloR + maxHaloC);
         b += sizeof(double) * (size_t)(16 * kGWarps);  // reduction scratch
-        b += sizeof(int) * ((size_t)maxSellR + maxSellC + maxRpad + maxCpad + maxNSR + 1 + maxNSC + 1);
+        b += sizeof(int) * ((size_t)maxHaloR + maxHaloC + maxRpad + maxCpad + maxNSR + 1 + maxNSC + 1);
+        b += sizeof(unsigned short) * ((size_t)maxSellR + maxSellC);
+        b += (size_t)maxRpad + maxCpad;  // tail bytes
         return b + 64;
     }
 };
@@ -47,25 +57,35 @@ struct GroupPlan {
     GroupSmem sm{};
     std::vector<GroupCta> cta;
     DBuf<GroupCta> d_cta;
-    DBuf<int> sellR_src, sellR_idx, ptrR, slotR, sellC_src, sellC_idx, ptrC, slotC;
+    DBuf<int> sellR_src, sellR_idx, ptrR, slotR, haloR, sellC_src, sellC_idx, ptrC, slotC, haloC;
+    DBuf<unsigned char> tailR, tailC;
+    int totSellR = 0, totSellC = 0;
+    DBuf<double> gA, gAT;  // per resident group: matrix values in sliced-ELL order (streamed when !mats)
+    DBuf<double> gconst;   // per resident group and block: rl, ru, c, lb, ub by slot (when !mats)
     // per-launch workspace
-    int n_groups = 0;
+    int n_groups = 0, max_groups = 0;
     DBuf<double> gx, gx2, gxp, grc, gy, gyp, gray, part;
     DBuf<unsigned> bar;
     DBuf<int> queue, slot;
 };
 
 // ---- host: partition + sliced-ELL layout -----------------------------------------------------------------------
-// `ptr`/`idx` is CSR (for the row side) or CSC (for the column side) of the pattern; `count` rows (columns).
-// Returns per block: range, slot order (by length, longest first, stable), slice pointers and for every
-// sliced-ELL element the source position in the value array (-1 = padding) and the gathered index.
+// `ptr`/`idx` is CSR (for the row side) or CSC (for the column side) of the pattern; `count` rows (columns),
+// gathered indices range over `other`.  Per block: a contiguous range, its halo (sorted distinct gathered
+// indices), and a sliced-ELL layout over *slots*: a row longer than kSlotCap is cut into pieces that sit in
+// consecutive lanes of one slice (the head lane owns the row, a segmented warp reduction adds the pieces), so
+// no lane walks more than ~kSlotCap entries.  Rows are ordered by (pieces, length) so slices are nearly
+// rectangular.  Every element stores the source position in the value array (-1 = padding) and the halo
+// position of the gathered index.
+constexpr int kSlotCap = 8;
 struct SellSide {
-    std::vector<int> first, cnt, nslice, base, ecnt, ptr_base, slot_base;
-    std::vector<int> src, idx, ptr, slot;
+    std::vector<int> first, cnt, nslice, base, ecnt, ptr_base, slot_base, halo_base, halo_cnt;
+    std::vector<int> src, idx, ptr, slot, halo;
+    std::vector<unsigned char> tail;  // per slot: lanes that follow in the same row group
 };
-inline void build_sell_side(int count, const int *ptr, const int *idx, const int *srcmap, int G, SellSide &o) {
+inline void build_sell_side(int count, int other, const int *ptr, const int *idx, const int *srcmap, int G, SellSide &o) {
     o = SellSide();
-    // balanced contiguous split by (length + 2) weight
+    std::vector<int> pos(other, -1);
     std::vector<long long> pre(count + 1, 0);
     for (int i = 0; i < count; ++i) pre[i + 1] = pre[i] + (ptr[i + 1] - ptr[i]) + 2;
     int start = 0;
@@ -79,11 +99,54 @@ inline void build_sell_side(int count, const int *ptr, const int *idx, const int
             end = std::max(start, std::min(end, count));
         }
         const int nloc = end - start;
+        std::vector<int> hl;
+        for (int k = ptr[start]; k < ptr[end]; ++k)
+            if (pos[idx[k]] < 0) {
+                pos[idx[k]] = 0;
+                hl.push_back(idx[k]);
+            }
+        std::sort(hl.begin(), hl.end());
+        for (size_t t = 0; t < hl.size(); ++t) pos[hl[t]] = (int)t;
+        o.halo_base.push_back((int)o.halo.size());
+        o.halo_cnt.push_back((int)hl.size());
+        o.halo.insert(o.halo.end(), hl.begin(), hl.end());
+        auto pieces = [&](int i) {
+            const int L = ptr[i + 1] - ptr[i];
+            return std::max(1, std::min(32, (L + kSlotCap - 1) / kSlotCap));
+        };
         std::vector<int> order(nloc);
         for (int i = 0; i < nloc; ++i) order[i] = start + i;
-        std::stable_sort(order.begin(), order.end(),
-                         [&](int a, int b) { return (ptr[a + 1] - ptr[a]) > (ptr[b + 1] - ptr[b]); });
-        const int ns = (nloc + 31) / 32;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const int pa = pieces(a), pb = pieces(b);
+            if (pa != pb) return pa > pb;
+            return (ptr[a + 1] - ptr[a]) > (ptr[b + 1] - ptr[b]);
+        });
+        // pack whole rows into 32-lane slices
+        struct Lane {
+            int row, k0, k1, tail;
+            bool head;
+        };
+        std::vector<std::vector<Lane>> slices;
+        std::vector<Lane> cur;
+        for (int i : order) {
+            const int pc = pieces(i), L = ptr[i + 1] - ptr[i];
+            const int plen = (L + pc - 1) / pc;
+            if ((int)cur.size() + pc > 32) {
+                slices.push_back(cur);
+                cur.clear();
+            }
+            for (int q = 0; q < pc; ++q) {
+                Lane ln;
+                ln.row = i;
+                ln.k0 = ptr[i] + std::min(L, q * plen);
+                ln.k1 = ptr[i] + std::min(L, (q + 1) * plen);
+                ln.tail = pc - 1 - q;
+                ln.head = q == 0;
+                cur.push_back(ln);
+            }
+        }
+        if (!cur.empty()) slices.push_back(cur);
+        const int ns = (int)slices.size();
         o.first.push_back(start);
         o.cnt.push_back(nloc);
         o.nslice.push_back(ns);
@@ -93,25 +156,30 @@ inline void build_sell_side(int count, const int *ptr, const int *idx, const int
         int cols = 0;
         o.ptr.push_back(0);
         for (int q = 0; q < ns; ++q) {
-            const int lead = order[q * 32];
-            const int len = ptr[lead + 1] - ptr[lead];
+            int len = 0;
+            for (const Lane &ln : slices[q]) len = std::max(len, ln.k1 - ln.k0);
             const size_t at = o.src.size();
             o.src.resize(at + (size_t)len * 32, -1);
             o.idx.resize(at + (size_t)len * 32, 0);
             for (int lane = 0; lane < 32; ++lane) {
-                const int sl = q * 32 + lane;
-                if (sl >= nloc) continue;
-                const int i = order[sl];
-                for (int k = ptr[i]; k < ptr[i + 1]; ++k) {
-                    o.src[at + (size_t)(k - ptr[i]) * 32 + lane] = srcmap ? srcmap[k] : k;
-                    o.idx[at + (size_t)(k - ptr[i]) * 32 + lane] = idx[k];
+                if (lane < (int)slices[q].size()) {
+                    const Lane &ln = slices[q][lane];
+                    for (int k = ln.k0; k < ln.k1; ++k) {
+                        o.src[at + (size_t)(k - ln.k0) * 32 + lane] = srcmap ? srcmap[k] : k;
+                        o.idx[at + (size_t)(k - ln.k0) * 32 + lane] = pos[idx[k]];
+                    }
+                    o.slot.push_back(ln.head ? ln.row : -1);
+                    o.tail.push_back((unsigned char)ln.tail);
+                } else {
+                    o.slot.push_back(-1);
+                    o.tail.push_back(0);
                 }
             }
             cols += len;
             o.ptr.push_back(cols);
         }
-        for (int sl = 0; sl < ns * 32; ++sl) o.slot.push_back(sl < nloc ? order[sl] : -1);
         o.ecnt.push_back(cols * 32);
+        for (int t : hl) pos[t] = -1;
         start = end;
     }
 }
@@ -120,12 +188,16 @@ inline void build_sell_side(int count, const int *ptr, const int *idx, const int
 struct GroupArgs {
     LpView v;
     const GroupCta *cta;
-    const int *sellR_src, *sellR_idx, *ptrR, *slotR, *sellC_src, *sellC_idx, *ptrC, *slotC;
+    const int *sellR_src, *sellR_idx, *ptrR, *slotR, *haloR, *sellC_src, *sellC_idx, *ptrC, *slotC, *haloC;
+    const unsigned char *tailR, *tailC;
+    double *gA, *gAT;  // [groups][totSellR], [groups][totSellC]
+    double *gconst;    // [groups][G][2 maxRpad + 3 maxCpad]
+    int totSellR, totSellC;
     double *gx, *gx2, *gxp, *grc, *gy, *gyp, *gray, *part;
     unsigned *bar;
     int *queue, *slot;
     int G, Buser;
-    long long max_iter;
+    long long max_iter, budget;  // per-LP iteration limit; iterations one launch may add to an LP
     int steps;
     GroupSmem sm;
 };
@@ -139,7 +211,10 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
 template <bool CLUSTER>
 __device__ __forceinline__ void group_sync(unsigned *bar, unsigned &epoch, int G) {
     if (CLUSTER) {
-        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        // one fence per block (not per warp): the block barrier orders every thread's stores before thread 0's fence
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence();
+        asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     } else {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -259,7 +334,38 @@ __device__ inline void group_decide(ScenState &st, const DevParams &P, const dou
     }
 }
 
-template <bool CLUSTER>
+
+// halo copy: shared[t] = vec[list[t]] (list sorted => neighbouring lanes hit neighbouring sectors)
+__device__ __forceinline__ void halo_fetch(double *__restrict__ dst, const double *__restrict__ vec,
+                                           const int *__restrict__ list, int cnt) {
+    for (int t = threadIdx.x; t < cnt; t += kGThreads) dst[t] = __ldcg(vec + list[t]);
+    __syncthreads();
+}
+
+// one sliced-ELL row (column) of this lane: sum_k val[k] * halo[idx[k]]
+// segmented suffix sum over the lanes of one row group: the head lane (largest tail) ends with the row total
+__device__ __forceinline__ double seg_reduce(double v, int tail) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_down_sync(0xffffffffu, v, o);
+        if (tail >= o) v += u;
+    }
+    return v;
+}
+template <bool MATS>
+__device__ __forceinline__ double sell_dot(const double *__restrict__ sval, const double *__restrict__ gval,
+                                           const unsigned short *__restrict__ idx, const double *__restrict__ halo,
+                                           int p0, int len, int tail, bool split) {
+    double acc = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < len; ++k) {
+        const double a = MATS ? sval[p0 + k * 32] : __ldcg(gval + p0 + k * 32);
+        acc += a * halo[idx[p0 + k * 32]];
+    }
+    return split ? seg_reduce(acc, tail) : acc;
+}
+
+template <bool CLUSTER, bool MATS>
 __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const LpView &v = a.v;
@@ -270,33 +376,50 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
     const GroupCta d = a.cta[rank];
     // ---- carve shared memory
     double *a_val = reinterpret_cast<double *>(smem_raw);
-    double *t_val = a_val + a.sm.maxSellR;
-    double *sy = t_val + a.sm.maxSellC;
+    double *t_val = a_val + (MATS ? a.sm.maxSellR : 0);
+    double *sy = t_val + (MATS ? a.sm.maxSellC : 0);
     double *sya = sy + a.sm.maxRpad;
-    double *srl = sya + a.sm.maxRpad;
-    double *sru = srl + a.sm.maxRpad;
-    double *sx = sru + a.sm.maxRpad;
+    double *sx = sya + a.sm.maxRpad;
     double *sxa = sx + a.sm.maxCpad;
-    double *scc = sxa + a.sm.maxCpad;
+    double *cst = MATS ? sxa + a.sm.maxCpad
+                       : a.gconst + ((size_t)(blockIdx.x / a.G) * a.G + blockIdx.x % a.G) * (2 * (size_t)a.sm.maxRpad + 3 * (size_t)a.sm.maxCpad);
+    double *srl = cst;
+    double *sru = srl + a.sm.maxRpad;
+    double *scc = sru + a.sm.maxRpad;
     double *slb = scc + a.sm.maxCpad;
     double *sub = slb + a.sm.maxCpad;
-    double *scratch = sub + a.sm.maxCpad;
-    int *a_idx = reinterpret_cast<int *>(scratch + 16 * kGWarps);
-    int *t_idx = a_idx + a.sm.maxSellR;
-    int *rmap = t_idx + a.sm.maxSellC;
+    double *hx = MATS ? sub + a.sm.maxCpad : sxa + a.sm.maxCpad;  // halo of the row side: entries of xbar
+    double *hy = hx + a.sm.maxHaloR;       // halo of the column side: entries of y
+    double *scratch = hy + a.sm.maxHaloC;
+    int *listR = reinterpret_cast<int *>(scratch + 16 * kGWarps);
+    int *listC = listR + a.sm.maxHaloR;
+    int *rmap = listC + a.sm.maxHaloC;
     int *cmap = rmap + a.sm.maxRpad;
     int *ptrR = cmap + a.sm.maxCpad;
     int *ptrC = ptrR + a.sm.maxNSR + 1;
+    unsigned short *a_idx = reinterpret_cast<unsigned short *>(ptrC + a.sm.maxNSC + 1);
+    unsigned short *t_idx = a_idx + a.sm.maxSellR;
+    unsigned char *tailR = reinterpret_cast<unsigned char *>(t_idx + a.sm.maxSellC);
+    unsigned char *tailC = tailR + a.sm.maxRpad;
     __shared__ ScenState st;
+    __shared__ double wtab[kMaxSteps];
     __shared__ DevParams P;
     __shared__ double qred[Q_COUNT];
     __shared__ int s_cur;
 
     // ---- pattern (shared by every LP of the batch): staged once
-    for (int i = tid; i < d.sellR_cnt; i += kGThreads) a_idx[i] = a.sellR_idx[d.sellR_base + i];
-    for (int i = tid; i < d.sellC_cnt; i += kGThreads) t_idx[i] = a.sellC_idx[d.sellC_base + i];
-    for (int i = tid; i < d.nSR * 32; i += kGThreads) rmap[i] = a.slotR[d.slotR_base + i];
-    for (int i = tid; i < d.nSC * 32; i += kGThreads) cmap[i] = a.slotC[d.slotC_base + i];
+    for (int i = tid; i < d.sellR_cnt; i += kGThreads) a_idx[i] = (unsigned short)a.sellR_idx[d.sellR_base + i];
+    for (int i = tid; i < d.sellC_cnt; i += kGThreads) t_idx[i] = (unsigned short)a.sellC_idx[d.sellC_base + i];
+    for (int i = tid; i < d.haloR_cnt; i += kGThreads) listR[i] = a.haloR[d.haloR_base + i];
+    for (int i = tid; i < d.haloC_cnt; i += kGThreads) listC[i] = a.haloC[d.haloC_base + i];
+    for (int i = tid; i < d.nSR * 32; i += kGThreads) {
+        rmap[i] = a.slotR[d.slotR_base + i];
+        tailR[i] = a.tailR[d.slotR_base + i];
+    }
+    for (int i = tid; i < d.nSC * 32; i += kGThreads) {
+        cmap[i] = a.slotC[d.slotC_base + i];
+        tailC[i] = a.tailC[d.slotC_base + i];
+    }
     for (int i = tid; i <= d.nSR; i += kGThreads) ptrR[i] = a.ptrR[d.ptrR_base + i];
     for (int i = tid; i <= d.nSC; i += kGThreads) ptrC[i] = a.ptrC[d.ptrC_base + i];
     if (tid == 0) P = *v.prm;
@@ -305,6 +428,8 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
     double *gx = a.gx + (size_t)grp * n, *gx2 = a.gx2 + (size_t)grp * n, *gxp = a.gxp + (size_t)grp * n,
            *grc = a.grc + (size_t)grp * n;
     double *gy = a.gy + (size_t)grp * m, *gyp = a.gyp + (size_t)grp * m, *gray = a.gray + (size_t)grp * m;
+    double *gA = a.gA + (size_t)grp * a.totSellR + d.sellR_base;    // this block's slice
+    double *gAT = a.gAT + (size_t)grp * a.totSellC + d.sellC_base;
     double *part = a.part + (size_t)grp * G * Q_COUNT;
     unsigned *bar = a.bar + grp;
     unsigned epoch = 0;
@@ -318,65 +443,83 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
         const int s = s_cur;
         if (s >= a.Buser) break;
         if (tid == 0) st = v.state[s];
+        __syncthreads();
+        if (st.status >= 0) continue;  // already finished (hybrid hand-over from the streaming engine): uniform in the group
         // ---- stage the values of this LP
         for (int i = tid; i < d.sellR_cnt; i += kGThreads) {
             const int src = a.sellR_src[d.sellR_base + i];
-            a_val[i] = src >= 0 ? v.A[(size_t)src * B + s] : 0.0;
+            const double val = src >= 0 ? v.A[(size_t)src * B + s] : 0.0;
+            if (MATS)
+                a_val[i] = val;
+            else
+                gA[i] = val;
         }
         for (int i = tid; i < d.sellC_cnt; i += kGThreads) {
             const int src = a.sellC_src[d.sellC_base + i];
-            t_val[i] = src >= 0 ? v.AT[(size_t)src * B + s] : 0.0;
+            const double val = src >= 0 ? v.AT[(size_t)src * B + s] : 0.0;
+            if (MATS)
+                t_val[i] = val;
+            else
+                gAT[i] = val;
         }
         for (int sl = tid; sl < d.nSR * 32; sl += kGThreads) {
             const int gi = rmap[sl];
-            double y0 = 0.0, l = -INFINITY, u = INFINITY;
+            double y0 = 0.0, ya0 = 0.0, l = -INFINITY, u = INFINITY;
             if (gi >= 0) {
                 const size_t e = (size_t)gi * B + s;
                 y0 = v.y[e];
+                ya0 = v.ya[e];
                 l = v.rls[e];
                 u = v.rus[e];
                 gy[gi] = y0;
             }
             sy[sl] = y0;
-            sya[sl] = y0;
+            sya[sl] = ya0;
             srl[sl] = l;
             sru[sl] = u;
         }
         for (int sl = tid; sl < d.nSC * 32; sl += kGThreads) {
             const int gj = cmap[sl];
-            double x0 = 0.0, c = 0.0, l = 0.0, u = 0.0;
+            double x0 = 0.0, xa0 = 0.0, c = 0.0, l = 0.0, u = 0.0;
             if (gj >= 0) {
                 const size_t e = (size_t)gj * B + s;
                 x0 = v.x[e];
+                xa0 = v.xa[e];
                 c = v.cs[e];
                 l = v.lbs[e];
                 u = v.ubs[e];
             }
             sx[sl] = x0;
-            sxa[sl] = x0;
+            sxa[sl] = xa0;
             scc[sl] = c;
             slb[sl] = l;
             sub[sl] = u;
         }
         group_sync<CLUSTER>(bar, epoch, G);
 
-        const bool live0 = st.status < 0;
-        long long it = 0;
-        bool done = !live0;
-        while (!done && it < a.max_iter) {
+        const bool live0 = true;
+        long long it = st.total;
+        const long long it_stop = it + a.budget;
+        bool done = false;
+        while (!done && it < a.max_iter && it < it_stop) {
+            // step sizes and Halpern weights of this block of iterations (they only change at its last check)
+            const double tau = st.eta / st.omega, sigma = st.eta * st.omega, isig = 1.0 / sigma;
+            if (tid < a.steps) {
+                const int kk = st.k0 + tid + 1;
+                wtab[tid] = (double)kk / ((double)kk + 1.0);
+            }
+            __syncthreads();
             for (int j = 0; j < a.steps && !done; ++j) {
                 const bool check = (j == 0 || j == a.steps - 1);
-                const double tau = st.eta / st.omega, sigma = st.eta * st.omega, isig = 1.0 / sigma;
-                const int kk = st.k0 + j + 1;
-                const double w = (double)kk / ((double)kk + 1.0);
+                const double w = wtab[j];
                 if (!check) {
                     // ------------------------------ primal half
+                    halo_fetch(hy, gy, listC, d.haloC_cnt);
                     for (int q = warp; q < d.nSC; q += kGWarps) {
                         const int sl = q * 32 + lane;
                         const int p0 = ptrC[q] * 32 + lane, len = ptrC[q + 1] - ptrC[q];
-                        double acc = 0.0;
-#pragma unroll 4
-                        for (int k = 0; k < len; ++k) acc += t_val[p0 + k * 32] * ldx(gy + t_idx[p0 + k * 32]);
+                        const int tl = tailC[sl];
+                        const double acc = sell_dot<MATS>(t_val, gAT, t_idx, hy, p0, len, tl, __any_sync(0xffffffffu, tl));
                         const int gj = cmap[sl];
                         const double xv = sx[sl];
                         const double xpv = fmin(fmax(xv - tau * (scc[sl] - acc), slb[sl]), sub[sl]);
@@ -386,12 +529,12 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                     }
                     group_sync<CLUSTER>(bar, epoch, G);
                     // ------------------------------ dual half
+                    halo_fetch(hx, gx, listR, d.haloR_cnt);
                     for (int q = warp; q < d.nSR; q += kGWarps) {
                         const int sl = q * 32 + lane;
                         const int p0 = ptrR[q] * 32 + lane, len = ptrR[q + 1] - ptrR[q];
-                        double acc = 0.0;
-#pragma unroll 4
-                        for (int k = 0; k < len; ++k) acc += a_val[p0 + k * 32] * ldx(gx + a_idx[p0 + k * 32]);
+                        const int tl = tailR[sl];
+                        const double acc = sell_dot<MATS>(a_val, gA, a_idx, hx, p0, len, tl, __any_sync(0xffffffffu, tl));
                         const int gi = rmap[sl];
                         const double yv = sy[sl];
                         const double t = acc - yv * isig;
@@ -405,14 +548,16 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                     continue;
                 }
                 // ================================== check iteration ==========================================
+                // (second operand of the two-vector products is gathered straight from L2: rare, so slow is fine)
                 double acc[Q_COUNT];
 #pragma unroll
                 for (int i = 0; i < Q_COUNT; ++i) acc[i] = 0.0;
+                halo_fetch(hy, gy, listC, d.haloC_cnt);
                 for (int q = warp; q < d.nSC; q += kGWarps) {
                     const int sl = q * 32 + lane;
                     const int p0 = ptrC[q] * 32 + lane, len = ptrC[q + 1] - ptrC[q];
-                    double s1 = 0.0;
-                    for (int k = 0; k < len; ++k) s1 += t_val[p0 + k * 32] * ldx(gy + t_idx[p0 + k * 32]);
+                    const int tl = tailC[sl];
+                    const double s1 = sell_dot<MATS>(t_val, gAT, t_idx, hy, p0, len, tl, true);
                     const int gj = cmap[sl];
                     if (gj < 0) continue;
                     const double cj = scc[sl], xv = sx[sl];
@@ -427,16 +572,19 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                 }
                 group_sync<CLUSTER>(bar, epoch, G);
                 const double inv_sb = 1.0 / st.sb, inv_sc = 1.0 / st.sc;
+                halo_fetch(hx, gx, listR, d.haloR_cnt);
                 for (int q = warp; q < d.nSR; q += kGWarps) {
                     const int sl = q * 32 + lane;
                     const int p0 = ptrR[q] * 32 + lane, len = ptrR[q + 1] - ptrR[q];
                     double s1 = 0.0, s2 = 0.0;
                     for (int k = 0; k < len; ++k) {
-                        const double av = a_val[p0 + k * 32];
-                        const int ci = a_idx[p0 + k * 32];
-                        s1 += av * ldx(gx + ci);
-                        s2 += av * ldx(gx2 + ci);
+                        const double av = MATS ? a_val[p0 + k * 32] : __ldcg(gA + p0 + k * 32);
+                        const int hp = a_idx[p0 + k * 32];
+                        s1 += av * hx[hp];
+                        s2 += av * __ldcg(gx2 + listR[hp]);
                     }
+                    s1 = seg_reduce(s1, tailR[sl]);
+                    s2 = seg_reduce(s2, tailR[sl]);
                     const int gi = rmap[sl];
                     if (gi < 0) continue;
                     const double yv = sy[sl];
@@ -461,16 +609,19 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                     acc[Q_RAY_MAX] = fmax(acc[Q_RAY_MAX], fabs(dd * dri));
                 }
                 group_sync<CLUSTER>(bar, epoch, G);
+                halo_fetch(hy, gyp, listC, d.haloC_cnt);
                 for (int q = warp; q < d.nSC; q += kGWarps) {
                     const int sl = q * 32 + lane;
                     const int p0 = ptrC[q] * 32 + lane, len = ptrC[q + 1] - ptrC[q];
                     double s1 = 0.0, s2 = 0.0;
                     for (int k = 0; k < len; ++k) {
-                        const double tv = t_val[p0 + k * 32];
-                        const int ri = t_idx[p0 + k * 32];
-                        s1 += tv * ldx(gyp + ri);
-                        s2 += tv * ldx(gray + ri);
+                        const double tv = MATS ? t_val[p0 + k * 32] : __ldcg(gAT + p0 + k * 32);
+                        const int hp = t_idx[p0 + k * 32];
+                        s1 += tv * hy[hp];
+                        s2 += tv * __ldcg(gray + listC[hp]);
                     }
+                    s1 = seg_reduce(s1, tailC[sl]);
+                    s2 = seg_reduce(s2, tailC[sl]);
                     const int gj = cmap[sl];
                     if (gj < 0) continue;
                     const double rc = scc[sl] - s1;
