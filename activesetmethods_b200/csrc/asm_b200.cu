@@ -785,6 +785,9 @@ void asm_lp_default_params(asm_lp_params *p) {
     p->pid_kp = 0.5;
     p->pid_ki = 0.0;
     p->pid_kd = 0.0;
+    p->engine = 0;
+    p->group_size = 0;
+    p->hand_over = 0.5;
 }
 
 // ---- generic LP -------------------------------------------------------------------------------------------------

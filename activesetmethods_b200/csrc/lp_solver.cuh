@@ -1088,7 +1088,10 @@ class LpSolver {
         const unsigned grid = (unsigned)(pl.n_groups * pl.G);
         const void *fn = group_kernel(pl.cluster, pl.sm.mats != 0);
         void *args[] = {(void *)&a};
+        // plans of different group sizes share the kernel: the attribute must match this launch
+        ASM_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (pl.cluster) {
+            ASM_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, pl.G > 8 ? 1 : 0));
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
             cfg.blockDim = dim3(kGThreads);
@@ -1170,7 +1173,7 @@ class LpSolver {
         //         2 = persistent on-chip group kernel, 0 = group kernel when the LP fits, else streaming
         // engine 0: a single LP runs on the group kernel; a batch streams until a quarter of it is left, then the
         // stragglers finish on the group kernel, each to its own convergence
-        const int hand_over = Buser == 1 ? 0 : std::max(1, Buser / 4);
+        const int hand_over = Buser == 1 ? 0 : std::max(1, std::min(Buser, (int)(P.hand_over * Buser)));
         const bool plan_ok = P.engine != 1 && ensure_plan(P.group_size, P.engine == 2 ? Buser : std::max(1, hand_over)) == ASM_OK;
         if (P.engine == 2 && !plan_ok) return ensure_plan(P.group_size, Buser);
         const bool group_only = plan_ok && (P.engine == 2 || Buser == 1);

@@ -37,7 +37,7 @@ UNIT = "scenarios/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--case", default="case1354pegase")
@@ -214,7 +214,7 @@ def run_ours(a):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
-    from activesetmethods_b200 import capi
+    from activesetmethods_b200 import capi, shard
     from activesetmethods_b200.sublp import SubLp
     lib = capi.load()
     if lib.asm_device_count() < 1:
@@ -223,7 +223,7 @@ def run_ours(a):
 
     S = a.scenarios
     net = network(a.case)
-    ids = [1 + rank * S + s for s in range(S)]          # scenario id = seed
+    ids = shard.scenario_ids(rank, world, S)             # scenario id = seed
     mdl, d = linearise(net, ids)
     n, m, nnz = mdl.n, mdl.m, mdl.nnz
     lp = SubLp(n, m, mdl.j_str, d["xL"], d["xU"], d["gL"], d["gU"], batch=S, device=local, eps_rel=a.eps,
@@ -270,18 +270,10 @@ def run_ours(a):
             torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.max_over_ranks(x, device="cuda" if world > 1 else None)
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return shard.sum_over_ranks(x, device="cuda" if world > 1 else None)
 
     lp.update(hin["x"], hin["f"], hin["df"], hin["E"], hin["dE"], hdelta, False)   # inputs resident
     for _ in range(a.warmup):
@@ -302,10 +294,11 @@ def run_ours(a):
     eng = lp.engine_info()
     dev_s = max_over_ranks(dev_ms * 1e-3)
     # ---- end to end through the C ABI with pinned host buffers
+    e2e_steps = min(a.steps, 2)            # each step is a full cold solve of the batch: two are enough
     e2e_step()
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
+    for _ in range(e2e_steps):
         e2e_step()
     sync_all()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -315,7 +308,7 @@ def run_ours(a):
     its_sum = sum_over_ranks(float(sum(i["iterations"] for i in infos)))
     total_scen = S * world
     value = total_scen * a.steps / dev_s
-    e2e = total_scen * a.steps / e2e_s
+    e2e = total_scen * e2e_steps / e2e_s
     h2d = 8 * S * (2 * n + m + nnz + 2) + 8 * S * m          # sub_optimize inputs + nu
     d2h = 8 * S * (3 * n + m + 2 * m) + 4 * S + 8 * S * 2    # p, lambda, mu_U, mu_L, slacks, status, 2 merit scalars
 
@@ -369,7 +362,8 @@ def run_ours(a):
                        "l2": "no flush: the batch working set (%.0f MB) exceeds the 126 MB L2" %
                              (Bpad * (16 * nnz_csr + 64 * n + 48 * m) / 1e6),
                        "wall_s_resident": wall_resident},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clk,
         }
         if cpu is not None:

@@ -67,7 +67,9 @@ typedef struct asm_lp_params {
     int32_t engine;        /* 0 auto; 1 streaming kernels (one launch per half iteration, CUDA graph);       */
                            /* 2 persistent group kernel (LP resident in the shared memory of G blocks)       */
     int32_t group_size;    /* blocks per LP for engine 2 (0 = auto)                                          */
-    double reserved[3];
+    double hand_over;      /* engine 0 on a batch: fraction of the batch still running at which the          */
+                           /* streaming kernels hand the stragglers to the group kernel (default 0.5)        */
+    double reserved[2];
 } asm_lp_params;
 void asm_lp_default_params(asm_lp_params *p);
 
