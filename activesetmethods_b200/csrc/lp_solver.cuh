@@ -246,6 +246,35 @@ __global__ void __launch_bounds__(kThreads) k_prepare_finish(LpView v, int warm)
 }
 
 // =================================== PDHG iteration ========================================================
+// sum_k val[k] * vec[idx[k]] over [k0, k1) of one scenario lane, four entries in flight at a time; the adds keep
+// the sequential order, so the result is bit-identical to the plain loop.
+__device__ __forceinline__ double spmv_row(const double *__restrict__ val, const int *__restrict__ idx,
+                                           const double *__restrict__ vec, int k0, int k1, int B, int s) {
+    double a = 0.0;
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+        const int i0 = idx[k], i1 = idx[k + 1], i2 = idx[k + 2], i3 = idx[k + 3];
+        const double a0 = val[(int64_t)k * B + s], a1 = val[(int64_t)(k + 1) * B + s],
+                     a2 = val[(int64_t)(k + 2) * B + s], a3 = val[(int64_t)(k + 3) * B + s];
+        const double x0 = vec[(int64_t)i0 * B + s], x1 = vec[(int64_t)i1 * B + s], x2 = vec[(int64_t)i2 * B + s],
+                     x3 = vec[(int64_t)i3 * B + s];
+        a += a0 * x0;
+        a += a1 * x1;
+        a += a2 * x2;
+        a += a3 * x3;
+    }
+    if (k + 2 <= k1) {
+        const int i0 = idx[k], i1 = idx[k + 1];
+        const double a0 = val[(int64_t)k * B + s], a1 = val[(int64_t)(k + 1) * B + s];
+        const double x0 = vec[(int64_t)i0 * B + s], x1 = vec[(int64_t)i1 * B + s];
+        a += a0 * x0;
+        a += a1 * x1;
+        k += 2;
+    }
+    if (k < k1) a += val[(int64_t)k * B + s] * vec[(int64_t)idx[k] * B + s];
+    return a;
+}
+
 // Primal half: g = cs - A'y ; xp = proj_box(x - tau g) ; xbar = 2 xp - x ; Halpern x <- w xbar + (1-w) xa.
 // CHECK: keep xp, g and xbar, leave x untouched (k_apply finishes the step after the restart decision).
 template <bool BATCH, bool CHECK>
@@ -261,14 +290,15 @@ __global__ void __launch_bounds__(kThreads) k_primal(LpView v, int jit) {
     if (live) {
         for (int64_t j = mp.first; j < v.n; j += mp.stride) {
             const int64_t e = j * B + mp.s;
-            double a = 0.0;
             const int k1 = v.col_ptr[j + 1];
-            for (int k = v.col_ptr[j]; k < k1; ++k)
-                a += v.AT[(int64_t)k * B + mp.s] * v.y[(int64_t)v.row_idx[k] * B + mp.s];
-            const double cj = v.cs[e];
+            int k = v.col_ptr[j];
+            // the column's own operands first: their loads overlap the gather chain below (the kernel is bound by
+            // bytes in flight per SM, not by issue)
+            const double cj = v.cs[e], xv = v.x[e], lo = v.lbs[e], up = v.ubs[e];
+            const double xav = CHECK ? 0.0 : v.xa[e];
+            const double a = spmv_row(v.AT, v.row_idx, v.y, k, k1, B, mp.s);
             const double g = cj - a;
-            const double xv = v.x[e];
-            const double xpv = fmin(fmax(xv - tau * g, v.lbs[e]), v.ubs[e]);
+            const double xpv = fmin(fmax(xv - tau * g, lo), up);
             const double xb = 2.0 * xpv - xv;
             v.xbar[e] = xb;
             if (CHECK) {
@@ -279,7 +309,7 @@ __global__ void __launch_bounds__(kThreads) k_primal(LpView v, int jit) {
                 acc[1] += da * da;
                 acc[2] += cj * xpv;
             } else {
-                v.x[e] = w * xb + (1.0 - w) * v.xa[e];
+                v.x[e] = w * xb + (1.0 - w) * xav;
             }
         }
     }
@@ -304,15 +334,20 @@ __global__ void __launch_bounds__(kThreads) k_dual(LpView v, int jit) {
             const int64_t e = i * B + mp.s;
             double a = 0.0, ax = 0.0;
             const int k1 = v.row_ptr[i + 1];
-            for (int k = v.row_ptr[i]; k < k1; ++k) {
-                const double av = v.A[(int64_t)k * B + mp.s];
-                const int64_t ce = (int64_t)v.col_idx[k] * B + mp.s;
-                a += av * v.xbar[ce];
-                if (CHECK) ax += av * v.x[ce];
+            const int k0 = v.row_ptr[i];
+            const double yv = v.y[e], l = v.rls[e], u = v.rus[e];
+            const double yav = CHECK ? 0.0 : v.ya[e];
+            if (CHECK) {
+                for (int k = k0; k < k1; ++k) {
+                    const double av = v.A[(int64_t)k * B + mp.s];
+                    const int64_t ce = (int64_t)v.col_idx[k] * B + mp.s;
+                    a += av * v.xbar[ce];
+                    ax += av * v.x[ce];
+                }
+            } else {
+                a = spmv_row(v.A, v.col_idx, v.xbar, k0, k1, B, mp.s);
             }
-            const double yv = v.y[e];
             const double t = a - yv * isig;
-            const double l = v.rls[e], u = v.rus[e];
             const double ypv = t < l ? sigma * (l - t) : (t > u ? sigma * (u - t) : 0.0);
             if (CHECK) {
                 v.yp[e] = ypv;
@@ -327,11 +362,100 @@ __global__ void __launch_bounds__(kThreads) k_dual(LpView v, int jit) {
                 // dual objective: rl y+ + ru y- (scaled units; unused side may be infinite -> guard)
                 acc[4] += ypv > 0.0 ? l * ypv : (ypv < 0.0 ? u * ypv : 0.0);
             } else {
-                v.y[e] = w * (2.0 * ypv - yv) + (1.0 - w) * v.ya[e];
+                v.y[e] = w * (2.0 * ypv - yv) + (1.0 - w) * yav;
             }
         }
     }
     if (CHECK) block_reduce_store<BATCH, 5>(acc, 0u, v.partials, Q_DY2, B);
+}
+
+// ---- two scenarios per lane (B % 64 == 0): the plain half iterations are bound by the bytes a warp keeps in
+// flight along its dependent chain (pointer -> index -> gather), so every lane loads 16 bytes (scenarios 2t, 2t+1
+// are adjacent in the element-major layout) and a warp moves 512 B per load.  Loads are never gated on the
+// scenario's status; only the stores are.  grid (rows / 8, B / 64), block 256.
+struct Lane2 {
+    int s0;  // first scenario of the lane
+    int64_t first, stride;
+    __device__ __forceinline__ Lane2() {
+        s0 = (blockIdx.y * 32 + (threadIdx.x & 31)) * 2;
+        first = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+        stride = (int64_t)gridDim.x * kWarps;
+    }
+};
+__device__ __forceinline__ double2 ld2(const double *p, int64_t row, int B, int s0) {
+    return *reinterpret_cast<const double2 *>(p + row * B + s0);
+}
+__device__ __forceinline__ void st2(double *p, int64_t row, int B, int s0, double a, double b, bool la, bool lb) {
+    if (la && lb)
+        *reinterpret_cast<double2 *>(p + row * B + s0) = make_double2(a, b);
+    else if (la)
+        p[row * B + s0] = a;
+    else if (lb)
+        p[row * B + s0 + 1] = b;
+}
+__device__ __forceinline__ double2 spmv_row2(const double *__restrict__ val, const int *__restrict__ idx,
+                                             const double *__restrict__ vec, int k0, int k1, int B, int s0) {
+    double ax = 0.0, ay = 0.0;
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+        const int i0 = idx[k], i1 = idx[k + 1], i2 = idx[k + 2], i3 = idx[k + 3];
+        const double2 a0 = ld2(val, k, B, s0), a1 = ld2(val, k + 1, B, s0), a2 = ld2(val, k + 2, B, s0),
+                      a3 = ld2(val, k + 3, B, s0);
+        const double2 x0 = ld2(vec, i0, B, s0), x1 = ld2(vec, i1, B, s0), x2 = ld2(vec, i2, B, s0),
+                      x3 = ld2(vec, i3, B, s0);
+        ax += a0.x * x0.x; ay += a0.y * x0.y;
+        ax += a1.x * x1.x; ay += a1.y * x1.y;
+        ax += a2.x * x2.x; ay += a2.y * x2.y;
+        ax += a3.x * x3.x; ay += a3.y * x3.y;
+    }
+    for (; k < k1; ++k) {
+        const double2 a0 = ld2(val, k, B, s0), x0 = ld2(vec, idx[k], B, s0);
+        ax += a0.x * x0.x;
+        ay += a0.y * x0.y;
+    }
+    return make_double2(ax, ay);
+}
+__global__ void __launch_bounds__(kThreads) k_primal2(LpView v, int jit) {
+    Lane2 mp;
+    const int B = v.B, s0 = mp.s0;
+    const ScenState *sa = v.state + s0, *sb = sa + 1;
+    const bool la = sa->status < 0, lb = sb->status < 0;
+    const double ta = sa->eta / sa->omega, tb = sb->eta / sb->omega;
+    const int ka = sa->k0 + jit + 1, kb = sb->k0 + jit + 1;
+    const double wa = (double)ka / ((double)ka + 1.0), wb = (double)kb / ((double)kb + 1.0);
+    if (!__any_sync(0xffffffffu, la || lb)) return;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int k0 = v.col_ptr[j], k1 = v.col_ptr[j + 1];
+        const double2 c = ld2(v.cs, j, B, s0), x = ld2(v.x, j, B, s0), lo = ld2(v.lbs, j, B, s0),
+                      up = ld2(v.ubs, j, B, s0), xa = ld2(v.xa, j, B, s0);
+        const double2 a = spmv_row2(v.AT, v.row_idx, v.y, k0, k1, B, s0);
+        const double pa = fmin(fmax(x.x - ta * (c.x - a.x), lo.x), up.x);
+        const double pb = fmin(fmax(x.y - tb * (c.y - a.y), lo.y), up.y);
+        const double ba = 2.0 * pa - x.x, bb = 2.0 * pb - x.y;
+        st2(v.xbar, j, B, s0, ba, bb, la, lb);
+        st2(v.x, j, B, s0, wa * ba + (1.0 - wa) * xa.x, wb * bb + (1.0 - wb) * xa.y, la, lb);
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_dual2(LpView v, int jit) {
+    Lane2 mp;
+    const int B = v.B, s0 = mp.s0;
+    const ScenState *sa = v.state + s0, *sb = sa + 1;
+    const bool la = sa->status < 0, lb = sb->status < 0;
+    const double ga = la ? sa->eta * sa->omega : 1.0, gb = lb ? sb->eta * sb->omega : 1.0;
+    const double ia = 1.0 / ga, ib = 1.0 / gb;
+    const int ka = sa->k0 + jit + 1, kb = sb->k0 + jit + 1;
+    const double wa = (double)ka / ((double)ka + 1.0), wb = (double)kb / ((double)kb + 1.0);
+    if (!__any_sync(0xffffffffu, la || lb)) return;
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int k0 = v.row_ptr[i], k1 = v.row_ptr[i + 1];
+        const double2 y = ld2(v.y, i, B, s0), l = ld2(v.rls, i, B, s0), u = ld2(v.rus, i, B, s0),
+                      ya = ld2(v.ya, i, B, s0);
+        const double2 a = spmv_row2(v.A, v.col_idx, v.xbar, k0, k1, B, s0);
+        const double t0 = a.x - y.x * ia, t1 = a.y - y.y * ib;
+        const double pa = t0 < l.x ? ga * (l.x - t0) : (t0 > u.x ? ga * (u.x - t0) : 0.0);
+        const double pb = t1 < l.y ? gb * (l.y - t1) : (t1 > u.y ? gb * (u.y - t1) : 0.0);
+        st2(v.y, i, B, s0, wa * (2.0 * pa - y.x) + (1.0 - wa) * ya.x, wb * (2.0 * pb - y.y) + (1.0 - wb) * ya.y, la, lb);
+    }
 }
 
 // Reduced costs of (xp, yp):  rc = cs - A'yp ; dual residual and column part of the dual objective.
@@ -816,6 +940,11 @@ class LpSolver {
                 ASM_KL(k_decide<<<B, kFinalThreads, 0, stream>>>(v, j, steps));
                 ASM_KB(k_apply, gm, v, kstep.p);
                 ASM_KL(k_after_apply<<<(B + 127) / 128, 128, 0, stream>>>(state.p, B));
+            } else if (B % 64 == 0) {
+                Geo g2c = gc, g2r = gr;
+                g2c.grid.y = g2r.grid.y = B / 64;
+                ASM_KL(k_primal2<<<g2c.grid, g2c.block, 0, stream>>>(v, j));
+                ASM_KL(k_dual2<<<g2r.grid, g2r.block, 0, stream>>>(v, j));
             } else {
                 ASM_KB2(k_primal, false, gc, v, j);
                 ASM_KB2(k_dual, false, gr, v, j);
@@ -1125,18 +1254,39 @@ class LpSolver {
         for (auto &s : live) s.status = -1;
         ASM_CK(cudaMemcpyAsync(state.p, live.data(), sizeof(ScenState) * B, cudaMemcpyHostToDevice, stream));
         float t = 0.f;
+        const bool wide = B % 64 == 0;
+        Geo g2c = gc, g2r = gr;
+        if (wide) g2c.grid.y = g2r.grid.y = B / 64;
+        auto primal = [&]() {
+            if (wide)
+                k_primal2<<<g2c.grid, g2c.block, 0, stream>>>(v, 1);
+            else if (B > 1)
+                k_primal<true, false><<<gc.grid, gc.block, 0, stream>>>(v, 1);
+            else
+                k_primal<false, false><<<gc.grid, gc.block, 0, stream>>>(v, 1);
+            ++launches;
+        };
+        auto dual = [&]() {
+            if (wide)
+                k_dual2<<<g2r.grid, g2r.block, 0, stream>>>(v, 1);
+            else if (B > 1)
+                k_dual<true, false><<<gr.grid, gr.block, 0, stream>>>(v, 1);
+            else
+                k_dual<false, false><<<gr.grid, gr.block, 0, stream>>>(v, 1);
+            ++launches;
+        };
         for (int w = 0; w < 3; ++w) {
-            ASM_KB2(k_primal, false, gc, v, 1);
-            ASM_KB2(k_dual, false, gr, v, 1);
+            primal();
+            dual();
         }
         ASM_CK(cudaEventRecord(ev0, stream));
-        for (int r = 0; r < reps; ++r) ASM_KB2(k_primal, false, gc, v, 1);
+        for (int r = 0; r < reps; ++r) primal();
         ASM_CK(cudaEventRecord(ev1, stream));
         ASM_CK(cudaEventSynchronize(ev1));
         ASM_CK(cudaEventElapsedTime(&t, ev0, ev1));
         if (primal_ms) *primal_ms = t / reps;
         ASM_CK(cudaEventRecord(ev0, stream));
-        for (int r = 0; r < reps; ++r) ASM_KB2(k_dual, false, gr, v, 1);
+        for (int r = 0; r < reps; ++r) dual();
         ASM_CK(cudaEventRecord(ev1, stream));
         ASM_CK(cudaEventSynchronize(ev1));
         ASM_CK(cudaEventElapsedTime(&t, ev0, ev1));

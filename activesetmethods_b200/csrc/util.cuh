@@ -245,6 +245,7 @@ __global__ void k_layout_out(const double *__restrict__ src, double *__restrict_
     }
 }
 
-inline int pad_batch(int b) { return b <= 1 ? 1 : ((b + 31) / 32) * 32; }
+// 1, or a multiple of 32; batches beyond 32 round up to 64 so that the two-scenarios-per-lane kernels apply
+inline int pad_batch(int b) { return b <= 1 ? 1 : (b <= 32 ? 32 : ((b + 63) / 64) * 64); }
 
 }  // namespace asmb

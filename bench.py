@@ -321,7 +321,7 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     Bp = lp.params  # noqa: F841
-    Bpad = ((S + 31) // 32) * 32 if S > 1 else 1
+    Bpad = 1 if S <= 1 else (32 if S <= 32 else ((S + 63) // 64) * 64)   # pad_batch() of csrc/util.cuh
     by_primal = Bpad * (8 * nnz_csr + 8 * m + 56 * n) + 4 * nnz_csr + 4 * (n + 1)
     by_dual = Bpad * (8 * nnz_csr + 8 * n + 40 * m) + 4 * nnz_csr + 4 * (m + 1)
     achieved = (by_primal + by_dual) / ((pm + dm) * 1e-3) / 1e9
