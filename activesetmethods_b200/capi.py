@@ -66,6 +66,9 @@ SIGNATURES = {
     "asm_lp_get_row_dual": (C.c_int, [_VP, c_double_p]),
     "asm_lp_get_col_dual": (C.c_int, [_VP, c_double_p, c_double_p]),
     "asm_lp_set_start": (C.c_int, [_VP, c_double_p, c_double_p]),
+    "asm_dist_unique_id": (C.c_int, [C.c_char_p]),
+    "asm_lp_dist_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, c_int64_p, c_int32_p, C.c_int32, C.c_int32,
+                                     C.c_char_p, C.c_int32, C.POINTER(_VP)]),
     "asm_slp_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, c_int64_p, c_int64_p, c_double_p, c_double_p,
                                  c_double_p, c_double_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_VP)]),
     "asm_slp_destroy": (None, [_VP]),

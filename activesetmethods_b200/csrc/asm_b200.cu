@@ -16,7 +16,7 @@
 #include <memory>
 #include <numeric>
 
-#include "lp_solver.cuh"
+#include "lp_dist.cuh"
 
 namespace asmb {
 
@@ -724,8 +724,11 @@ struct asm_slp {
     SlpHandle h;
 };
 struct asm_lp {
-    LpSolver s;
+    LpSolver own;
+    std::unique_ptr<DistLp> dist;  // row-partitioned instance (lp_dist.cuh); `s` is then its local block
+    LpSolver &s;
     int device = 0;
+    explicit asm_lp(bool partitioned) : dist(partitioned ? new DistLp() : nullptr), s(partitioned ? dist->lp : own) {}
     DBuf<double> stage;
     int put(const double *host, int64_t len, int S, double *dst) {
         if (len == 0) return ASM_OK;
@@ -799,7 +802,7 @@ int asm_lp_create(int32_t n_cols, int32_t n_rows, int64_t nnz, const int64_t *ro
     if (ndev == 0) return fail(ASM_E_CUDA, "no CUDA device: this library has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(ASM_E_INVALID, "device index out of range");
     ASM_CK(cudaSetDevice(device));
-    asm_lp *h = new (std::nothrow) asm_lp();
+    asm_lp *h = new (std::nothrow) asm_lp(false);
     if (!h) return fail(ASM_E_INVALID, "out of host memory");
     h->device = device;
     int rc = h->s.init(n_cols, n_rows, nnz, row_ptr, col_idx, batch, nullptr);
@@ -851,6 +854,7 @@ int asm_lp_solve(asm_lp *h, const asm_lp_params *params, asm_lp_info *info) {
         asm_lp_default_params(&d);
         params = &d;
     }
+    if (h->dist) return h->dist->solve(*params, info);
     return h->s.solve(*params, info);
 }
 int asm_lp_get_primal(asm_lp *h, double *x) {
@@ -879,6 +883,35 @@ int asm_lp_set_start(asm_lp *h, const double *x, const double *y) {
     if (y) ASM_TRY(h->put(y, h->s.m, h->s.Buser, h->s.yo.p));
     ASM_CK(cudaStreamSynchronize(h->s.stream));
     h->s.has_solution = true;
+    return ASM_OK;
+}
+
+// ---- row-partitioned single LP over NCCL ------------------------------------------------------------------------
+int asm_dist_unique_id(char *id128) {
+    if (!id128) return fail(ASM_E_INVALID, "null argument");
+    ASM_TRY(nccl().load());
+    NcclApi::UniqueId id;
+    ASM_NCCL(nccl().GetUniqueId(&id));
+    memcpy(id128, id.internal, sizeof id.internal);
+    return ASM_OK;
+}
+int asm_lp_dist_create(int32_t n_cols, int32_t n_rows_local, int64_t nnz_local, const int64_t *row_ptr,
+                       const int32_t *col_idx, int32_t rank, int32_t world, const char *id128, int32_t device,
+                       asm_lp **out) {
+    if (!out || !row_ptr || (nnz_local > 0 && !col_idx) || !id128) return fail(ASM_E_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = asm_device_count();
+    if (ndev == 0) return fail(ASM_E_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(ASM_E_INVALID, "device index out of range");
+    asm_lp *h = new (std::nothrow) asm_lp(true);
+    if (!h) return fail(ASM_E_INVALID, "out of host memory");
+    h->device = device;
+    int rc = h->dist->init(n_cols, n_rows_local, nnz_local, row_ptr, col_idx, rank, world, id128, device);
+    if (rc != ASM_OK) {
+        delete h;
+        return rc;
+    }
+    *out = h;
     return ASM_OK;
 }
 

@@ -26,6 +26,19 @@ def split_scenarios(total: int, world: int, first: int = 1):
     return out
 
 
+def row_blocks(row_ptr, world: int):
+    """Contiguous row blocks balanced by nonzeros (+2 per row) for the row-partitioned single instance
+    (SURVEY.md §8e): returns ``world + 1`` row offsets."""
+    rp = np.asarray(row_ptr, dtype=np.int64)
+    m = len(rp) - 1
+    weight = rp + 2 * np.arange(m + 1)
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(weight, weight[-1] * r / world)))
+    cuts.append(m)
+    return [min(max(c, cuts[i - 1] if i else 0), m) for i, c in enumerate(cuts)]
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Device-side time of a step = the slowest rank's."""
     import torch

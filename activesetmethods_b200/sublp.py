@@ -24,7 +24,7 @@ import numpy as np
 from . import capi
 from .capi import LP_OPTIMAL, LP_INFEASIBLE, LP_DUAL_INFEASIBLE, LP_ITERATION_LIMIT, LP_NUMERICAL_ERROR  # noqa: F401
 
-__all__ = ["SubLp", "B200LP", "LP_OPTIMAL", "LP_INFEASIBLE", "LP_DUAL_INFEASIBLE", "LP_ITERATION_LIMIT",
+__all__ = ["SubLp", "B200LP", "B200RowPartitionedLP", "LP_OPTIMAL", "LP_INFEASIBLE", "LP_DUAL_INFEASIBLE", "LP_ITERATION_LIMIT",
            "LP_NUMERICAL_ERROR"]
 
 
@@ -314,3 +314,50 @@ class B200LP:
         up = np.empty((self.batch, self.n))
         capi.check(self._lib.asm_lp_get_col_dual(self._h, capi.dptr(lo), capi.dptr(up)))
         return (lo[0], up[0]) if self.batch == 1 else (lo, up)
+
+
+class B200RowPartitionedLP(B200LP):
+    """One LP over several GPUs, one process per GPU (BASELINE config 4): rank ``rank`` of ``world``
+    owns a contiguous block of rows of ``K`` (balanced by nonzeros) with its duals; ``x`` is replicated and one NCCL
+    all-reduce of the partial ``K'y`` completes every PDHG iteration.  All ranks pass the *global* pattern and
+    data; each keeps its rows.  ``unique_id`` is the 128-byte id from :func:`nccl_unique_id` made on rank 0 and
+    shared by the host (e.g. ``torch.distributed.broadcast_object_list``).  ``optimize`` is collective."""
+
+    def __init__(self, n_cols, n_rows, row_ptr, col_idx, rank, world, unique_id, device=0, **lp_params):
+        from . import shard
+        self._lib = capi.load()
+        rp = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        ci = np.ascontiguousarray(col_idx, dtype=np.int32)
+        cuts = shard.row_blocks(rp, world)
+        self.r0, self.r1 = cuts[rank], cuts[rank + 1]
+        self.k0, self.k1 = int(rp[self.r0]), int(rp[self.r1])
+        self.rank, self.world = int(rank), int(world)
+        self.n, self.m, self.batch = int(n_cols), self.r1 - self.r0, 1
+        self.m_global, self.nnz_global = int(n_rows), int(rp[-1])
+        self.nnz = self.k1 - self.k0
+        lrp = np.ascontiguousarray(rp[self.r0:self.r1 + 1] - self.k0)
+        lci = np.ascontiguousarray(ci[self.k0:self.k1])
+        assert len(unique_id) == 128
+        self._h = C.c_void_p()
+        capi.check(self._lib.asm_lp_dist_create(self.n, self.m, self.nnz, lrp.ctypes.data_as(capi.c_int64_p),
+                                                lci.ctypes.data_as(capi.c_int32_p), self.rank, self.world,
+                                                bytes(unique_id), int(device), C.byref(self._h)))
+        self.params = capi.default_params(**lp_params)
+
+    def set_matrix_values(self, vals):
+        vals = capi.as_f64(vals, (self.nnz_global,))
+        super().set_matrix_values(np.ascontiguousarray(vals[self.k0:self.k1]))
+
+    def set_row_bounds(self, rl, ru):
+        rl, ru = capi.as_f64(rl, (self.m_global,)), capi.as_f64(ru, (self.m_global,))
+        super().set_row_bounds(np.ascontiguousarray(rl[self.r0:self.r1]), np.ascontiguousarray(ru[self.r0:self.r1]))
+
+    def set_start(self, x=None, y=None):
+        super().set_start(x, None if y is None else np.ascontiguousarray(capi.as_f64(y)[self.r0:self.r1]))
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL unique id (call on one rank, share with the others)."""
+    buf = C.create_string_buffer(128)
+    capi.check(capi.load().asm_dist_unique_id(buf))
+    return buf.raw

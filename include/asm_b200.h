@@ -116,6 +116,17 @@ int asm_lp_get_col_dual(asm_lp *h, double *dual_lb, double *dual_ub);
 /* warm start for the next solve (used when params.warm_start = 1); either pointer may be NULL */
 int asm_lp_set_start(asm_lp *h, const double *x, const double *y);
 
+/* ---- row-partitioned single LP (one very large instance over several GPUs) -----------------
+ * One process per GPU.  Rank g passes the CSR pattern of its contiguous row block (all n_cols columns); the
+ * setters above then take the local rows' values / row bounds and the replicated objective / column bounds;
+ * asm_lp_solve is collective (one ncclAllReduce of the partial K'y per PDHG iteration); asm_lp_get_primal returns
+ * the replicated x, asm_lp_get_row_dual the local rows' duals.  `id128` is a 128-byte NCCL unique id made by
+ * rank 0 with asm_dist_unique_id and handed to the other ranks by the host (torch.distributed / MPI / files). */
+int asm_dist_unique_id(char *id128);
+int asm_lp_dist_create(int32_t n_cols, int32_t n_rows_local, int64_t nnz_local, const int64_t *row_ptr,
+                       const int32_t *col_idx, int32_t rank, int32_t world, const char *id128, int32_t device,
+                       asm_lp **out);
+
 /* =======================================================================================================
  * 2. SLP fast path: the whole per-iteration sub-LP of the reference in three calls.
  *    Replaces compute_jacobian_matrix (common.jl:12-20), LpData (slp.jl:8-21), create_model!
