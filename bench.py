@@ -42,12 +42,16 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--case", default="case1354pegase")
     ap.add_argument("--scenarios", type=int, default=128, help="scenarios per GPU")
-    ap.add_argument("--eps", type=float, default=1e-6)
+    ap.add_argument("--eps", type=float, default=5e-7,
+                    help="relative KKT tolerance; 5e-7 keeps |pobj - dobj| / |obj| below the 1e-6 parity bar")
     ap.add_argument("--delta", type=float, default=1000.0, help="step bound (Line Search uses 1000, slp.jl:23)")
     ap.add_argument("--engine", type=int, default=0)
     ap.add_argument("--max-iter", type=int, default=4_000_000)
     ap.add_argument("--cpu-sample", type=int, default=2, help="scenarios of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="scenarios per reference step (0 = one per core)")
+    ap.add_argument("--workload", default="batch", choices=["batch", "single"],
+                    help="batch: scenario batch per GPU (default, the driver's metric); single: one instance "
+                         "(BASELINE config 4) -- group engine at N = 1, row-partitioned over NCCL at N > 1")
     return ap.parse_args()
 
 
@@ -374,10 +378,95 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_single(a):
+    """One sub-LP of one instance: `SubLp` (persistent group kernel) on one GPU, `B200RowPartitionedLP` on several."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        g.build()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("gloo")
+        dist.barrier()
+    from activesetmethods_b200 import capi, shard
+    from activesetmethods_b200.sublp import SubLp, B200RowPartitionedLP, nccl_unique_id
+    net = network(a.case)
+    mdl, d = linearise(net, [1])
+    n, m, nnz = mdl.n, mdl.m, mdl.nnz
+    lp = SubLp(n, m, mdl.j_str, d["xL"][0], d["xU"][0], d["gL"][0], d["gU"][0], batch=1, device=local, eps_rel=a.eps,
+               engine=a.engine, max_iter=a.max_iter)
+    args = (d["x"][0], d["f"][0], d["df"][0], d["E"][0], d["dE"][0], a.delta, False)
+    lp.update(*args)
+    if world == 1:
+        def step():
+            t0 = time.perf_counter()
+            out = lp.sub_optimize(*args)
+            return time.perf_counter() - t0, lp.last_info[0], lp.last_solve_timing()
+    else:
+        rp, ci, vals = lp.jacobian_csr()                       # device-assembled CSR of this linearisation
+        x = d["x"][0]
+        lb = np.maximum(-a.delta, d["xL"][0] - x)              # subproblem.jl:427-434
+        ub = np.minimum(a.delta, d["xU"][0] - x)
+        gl, gu, E = d["gL"][0], d["gU"][0], d["E"][0]
+        eq = gl == gu
+        rl = np.where(np.isfinite(gl), gl - E, -np.inf)        # subproblem.jl:461-484
+        ru = np.where(eq, gl - E, np.where(np.isfinite(gu), gu - E, np.inf))
+        ids = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        plp = B200RowPartitionedLP(n, m, rp, ci, rank, world, ids[0], device=local, eps_rel=a.eps, max_iter=a.max_iter)
+
+        def step():
+            dist.barrier()
+            t0 = time.perf_counter()
+            plp.set_matrix_values(vals)
+            plp.set_objective(d["df"][0], float(d["f"][0]))
+            plp.set_col_bounds(lb, ub)
+            plp.set_row_bounds(rl, ru)
+            info = plp.optimize()[0]
+            plp.primal()
+            plp.row_dual()
+            return time.perf_counter() - t0, info, (0.0, info["iterations"])
+    for _ in range(a.warmup):
+        step()
+    clocks = ClockSampler(local)
+    clocks.start()
+    tot, info, timing = 0.0, None, None
+    for _ in range(a.steps):
+        dt, info, timing = step()
+        tot += dt
+    clk = clocks.stop()
+    tot = shard.max_over_ranks(tot)
+    if rank == 0:
+        loop_ms, its = timing
+        b_iter = 24 * lp.nnz_csr + 76 * n + 60 * m + 8           # SURVEY.md 8(d), single LP
+        out = {"metric": "sub-LP solves/s, single instance (config 4)", "value": a.steps / tot, "unit": "sub-LP/s",
+               "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"{a.case} single instance, first SLP linearisation, step bound {a.delta:g}",
+                          "n": n, "m": m, "nnz_csr": lp.nnz_csr, "eps_rel": a.eps, "status": info["status"],
+                          "objective": info["objective"], "pdhg_iterations": info["iterations"],
+                          "engine": lp.engine_info() if world == 1 else "row-partitioned, NCCL all-reduce per iteration",
+                          "us_per_iteration": 1e6 * tot / a.steps / max(1, info["iterations"]),
+                          "algorithmic_GBs": b_iter * info["iterations"] / (tot / a.steps) / 1e9},
+               "e2e": {"value": a.steps / tot, "unit": "sub-LP/s", "h2d_bytes_per_step": 8 * (2 * n + m + nnz + 2),
+                       "d2h_bytes_per_step": 8 * (3 * n + 3 * m)},
+               "clocks": clk}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "single":
+        run_single(a)
     else:
         run_ours(a)
 
