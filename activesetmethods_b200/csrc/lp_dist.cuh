@@ -296,7 +296,7 @@ class DistLp {
         dp.verbose = P.verbose && rank == 0;
         ASM_CK(cudaMemcpyAsync(L.prm.p, &dp, sizeof dp, cudaMemcpyHostToDevice, stream));
         ASM_CK(cudaStreamSynchronize(stream));
-        ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && L.has_solution) ? 1 : 0));
+        ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && L.has_solution) ? (int)P.warm_start : 0));
         const int steps = std::max(2, (int)P.check_every);
         LpView v = L.view();
         const int n = L.n, m = L.m;

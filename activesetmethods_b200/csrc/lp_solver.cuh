@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kThreads) k_prepare_finish(LpView v, int warm)
         const double l = v.lbs[e] * sb, u = v.ubs[e] * sb;
         v.lbs[e] = l;
         v.ubs[e] = u;
-        double x0 = warm ? v.xo[e] / v.dc[e] * sb : 0.0;
+        double x0 = warm == 1 ? v.xo[e] / v.dc[e] * sb : 0.0;   // warm == 2: duals only
         x0 = fmin(fmax(x0, l), u);
         v.x[e] = x0;
         v.xa[e] = x0;
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(kFinalThreads) k_decide(LpView v, int jit, int
                 st.omega = exp(log(st.omega) + dlog);
                 st.e_prev = e;
             }
-            if (!(st.omega > st.omega0 * 1e-8 && st.omega < st.omega0 * 1e8)) {
+            if (!(st.omega > st.omega0 * 1e-16 && st.omega < st.omega0 * 1e16)) {
                 st.omega = st.omega0;
                 st.e_sum = 0.0;
                 st.e_prev = 0.0;
@@ -1317,7 +1317,7 @@ class LpSolver {
         *flag = Buser;
         ASM_CK(cudaMemcpyAsync(prm.p, pdp, sizeof dp, cudaMemcpyHostToDevice, stream));
         ASM_CK(cudaMemcpyAsync(n_active.p, flag, sizeof(int), cudaMemcpyHostToDevice, stream));
-        ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && has_solution) ? 1 : 0));
+        ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && has_solution) ? (int)P.warm_start : 0));
         const int steps = std::max(2, (int)P.check_every);
         // engine: 1 = one launch per half iteration (batch-streaming through HBM, CUDA graph per check period),
         //         2 = persistent on-chip group kernel, 0 = group kernel when the LP fits, else streaming

@@ -310,7 +310,7 @@ __device__ inline void group_decide(ScenState &st, const DevParams &P, const dou
                 st.omega = exp(log(st.omega) + dlog);
                 st.e_prev = e;
             }
-            if (!(st.omega > st.omega0 * 1e-8 && st.omega < st.omega0 * 1e8)) {
+            if (!(st.omega > st.omega0 * 1e-16 && st.omega < st.omega0 * 1e16)) {
                 st.omega = st.omega0;
                 st.e_sum = 0.0;
                 st.e_prev = 0.0;

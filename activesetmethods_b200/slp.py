@@ -160,8 +160,10 @@ class _Slp:
         pr, o = self.problem, self.options
         factory = o.external_optimizer
         if factory == "B200LP":
+            # like GLPK, which keeps its basis between the sub-LPs of a run (one glp_prob per SLP run, slp.jl:24),
+            # the engine starts every solve from the previous one's (p, lambda) unless told otherwise
             return SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, batch=1, device=o.device,
-                         **o.lp_options)
+                         **{"warm_start": 1, **o.lp_options})
         return factory(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U)
 
     # slp.jl:23-47

@@ -58,7 +58,7 @@ typedef struct asm_lp_params {
     int64_t max_iter;      /* PDHG iteration limit per LP (default 2 000 000)                               */
     int32_t check_every;   /* KKT / restart evaluation period in iterations (default 64)                   */
     int32_t ruiz_iters;    /* Ruiz equilibration passes before Pock-Chambolle (default 10)                 */
-    int32_t warm_start;    /* 1: start from the previous solve's (x, y) of this handle (default 0)         */
+    int32_t warm_start;    /* start from the previous solve of this handle: 1 = (x, y), 2 = y only; 0 = cold */
     int32_t verbose;       /* 1: print one line per restart check of scenario 0 to stderr                  */
     double restart_sufficient; /* 0.2  */
     double restart_necessary;  /* 0.8  */
