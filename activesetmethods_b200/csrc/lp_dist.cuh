@@ -58,21 +58,28 @@ inline NcclApi &nccl() {
 
 // ---- kernels of the partitioned iteration (single LP: B = 1) ----------------------------------------------------
 // column norms of the local row block (max or sum of |dr_i K_ij dc_j|), completed by an all-reduce
+// out[j] = scaled norm, out[n + j] = max |K_ij| of the original column (local rows)
 template <bool SUM>
 __global__ void __launch_bounds__(kThreads) k_col_norm_partial(LpView v, double *__restrict__ out) {
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < v.n; j += (int64_t)gridDim.x * blockDim.x) {
         const double dcj = v.dc[j];
-        double a = 0.0;
+        double a = 0.0, a0 = 0.0;
         for (int k = v.col_ptr[j]; k < v.col_ptr[j + 1]; ++k) {
-            const double t = fabs(v.vals[v.csc_src[k]] * v.dr[v.row_idx[k]] * dcj);
+            const double val = v.vals[v.csc_src[k]];
+            const double t = fabs(val * v.dr[v.row_idx[k]] * dcj);
             a = SUM ? a + t : fmax(a, t);
+            a0 = fmax(a0, fabs(val));
         }
         out[j] = a;
+        out[v.n + j] = a0;
     }
 }
-__global__ void k_inv_sqrt(const double *__restrict__ a, double *__restrict__ out, int64_t n) {
+// column scale factor from the completed norms; numerically empty columns keep scale 1 (see kTinyRel)
+__global__ void k_inv_sqrt(const double *__restrict__ a, const double *__restrict__ a0, const double *__restrict__ gmax,
+                           double *__restrict__ out, int64_t n) {
+    const double tiny = kTinyRel * gmax[0];
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
-        out[t] = a[t] > 0.0 ? 1.0 / sqrt(a[t]) : 1.0;
+        out[t] = (a[t] > 0.0 && a0[t] > tiny) ? 1.0 / sqrt(a[t]) : 1.0;
 }
 // t = K_g' w  (partial over the local rows); w is y, yp or the ray
 __global__ void __launch_bounds__(kThreads) k_aty(LpView v, const double *__restrict__ w, double *__restrict__ t) {
@@ -201,7 +208,7 @@ class DistLp {
     LpSolver lp;  // local row block: n columns, m_local rows
     int rank = 0, world = 1, device = 0;
     NcclApi::Comm comm = nullptr;
-    DBuf<double> t_part, t_full, qsum, qmax, psum;
+    DBuf<double> t_part, t_full, a0_full, qsum, qmax, psum;
     int64_t allreduces = 0;
 
     ~DistLp() {
@@ -220,8 +227,9 @@ class DistLp {
         NcclApi::UniqueId id;
         memcpy(id.internal, unique_id, sizeof id.internal);
         ASM_NCCL(nccl().CommInitRank(&comm, world, id, rank));
-        ASM_TRY(t_part.alloc(n));
-        ASM_TRY(t_full.alloc(n));
+        ASM_TRY(t_part.alloc(2 * (size_t)n));
+        ASM_TRY(t_full.alloc(2 * (size_t)n));
+        ASM_TRY(a0_full.alloc(n));
         ASM_TRY(qsum.alloc(Q_COUNT));
         ASM_TRY(qmax.alloc(2));
         ASM_TRY(psum.alloc(4));
@@ -243,6 +251,14 @@ class DistLp {
         const Geo gr = geo_for(m, 1), gc = geo_for(n, 1), gm = geo_for(std::max(n, m), 1);
         ASM_KL(k_fill<<<LpSolver::ew_grid(std::max(m, 1)), 1024, 0, stream>>>(L.dr.p, 1.0, m));
         ASM_KL(k_fill<<<LpSolver::ew_grid(n), 1024, 0, stream>>>(L.dc.p, 1.0, n));
+        {   // largest coefficient of the whole matrix (all ranks) and of every column
+            const Geo gz = geo_for(std::max<int64_t>(L.nnz, 1), 1);
+            ASM_KL(k_absmax<false><<<gz.grid, gz.block, 0, stream>>>(v, L.nnz));
+            ASM_KL(k_final_max<<<1, kFinalThreads, 0, stream>>>(L.partials.p, (int)gz.grid.x, 1, L.gmax.p));
+            ASM_TRY(allreduce(L.gmax.p, L.gmax.p, 1, NcclApi::kMax));
+            ASM_KL(k_col_norm_partial<false><<<gc.grid, gc.block, 0, stream>>>(v, t_part.p));
+            ASM_TRY(allreduce(t_part.p + n, a0_full.p, n, NcclApi::kMax));
+        }
         for (int it = 0; it <= ruiz_iters; ++it) {
             const bool pc = it == ruiz_iters;  // last pass: Pock-Chambolle (alpha = 1): 1-norms
             if (pc) {
@@ -253,7 +269,7 @@ class DistLp {
                 ASM_KL(k_col_norm_partial<false><<<gc.grid, gc.block, 0, stream>>>(v, t_part.p));
             }
             ASM_TRY(allreduce(t_part.p, t_full.p, n, pc ? NcclApi::kSum : NcclApi::kMax));
-            ASM_KL(k_inv_sqrt<<<LpSolver::ew_grid(n), 1024, 0, stream>>>(t_full.p, L.scf.p, n));
+            ASM_KL(k_inv_sqrt<<<LpSolver::ew_grid(n), 1024, 0, stream>>>(t_full.p, a0_full.p, L.gmax.p, L.scf.p, n));
             if (m) ASM_KL(k_mul_inplace<<<LpSolver::ew_grid(m), 1024, 0, stream>>>(L.dr.p, L.sr.p, m));
             ASM_KL(k_mul_inplace<<<LpSolver::ew_grid(n), 1024, 0, stream>>>(L.dc.p, L.scf.p, n));
         }

@@ -78,38 +78,61 @@ struct LpView {
     // results (unscaled)
     double *xo, *yo, *dlo, *dup;
     double *partials;
+    const double *gmax;  // per LP: max |K_ij| (rows / columns below kTinyRel * gmax are treated as empty by the scaling)
     ScenState *state;
     const DevParams *prm;
     int *n_active;
 };
 
 // =================================== preconditioning ======================================================
+// A row (column) whose largest coefficient is below kTinyRel times the largest of the matrix is numerically empty
+// (SLP produces them: the gradient of p^2 + q^2 <= s^2 at p, q ~ 1e-11).  Equilibrating it would multiply its
+// right-hand side by ~1e10 and wreck the bound / objective balance of the whole LP, so it keeps scale 1.
+constexpr double kTinyRel = 1e-8;
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_absmax(LpView v, int64_t nnz) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    double acc[1] = {0.0};
+    for (int64_t k = mp.first; k < nnz; k += mp.stride) acc[0] = fmax(acc[0], fabs(v.vals[k * B + mp.s]));
+    block_reduce_store<BATCH, 1>(acc, 1u, v.partials, 0, B);
+}
+__global__ void __launch_bounds__(kFinalThreads) k_final_max(const double *partials, int nbx, int B, double *out) {
+    const double q = final_reduce(partials, 0, nbx, B, blockIdx.x, true);
+    if (threadIdx.x == 0) out[blockIdx.x] = q;
+}
 template <bool BATCH, bool SUM>
 __global__ void __launch_bounds__(kThreads) k_ruiz_rows(LpView v) {
     Map<BATCH> mp;
     const int B = v.B;
+    const double tiny = kTinyRel * v.gmax[mp.s];
     for (int64_t i = mp.first; i < v.m; i += mp.stride) {
         const double dri = v.dr[i * B + mp.s];
-        double a = 0.0;
+        double a = 0.0, a0 = 0.0;
         for (int k = v.row_ptr[i]; k < v.row_ptr[i + 1]; ++k) {
-            double t = fabs(v.vals[(int64_t)k * B + mp.s] * dri * v.dc[(int64_t)v.col_idx[k] * B + mp.s]);
+            const double val = v.vals[(int64_t)k * B + mp.s];
+            double t = fabs(val * dri * v.dc[(int64_t)v.col_idx[k] * B + mp.s]);
             a = SUM ? a + t : fmax(a, t);
+            a0 = fmax(a0, fabs(val));
         }
-        v.sr[i * B + mp.s] = a > 0.0 ? 1.0 / sqrt(a) : 1.0;
+        v.sr[i * B + mp.s] = (a > 0.0 && a0 > tiny) ? 1.0 / sqrt(a) : 1.0;
     }
 }
 template <bool BATCH, bool SUM>
 __global__ void __launch_bounds__(kThreads) k_ruiz_cols(LpView v) {
     Map<BATCH> mp;
     const int B = v.B;
+    const double tiny = kTinyRel * v.gmax[mp.s];
     for (int64_t j = mp.first; j < v.n; j += mp.stride) {
         const double dcj = v.dc[j * B + mp.s];
-        double a = 0.0;
+        double a = 0.0, a0 = 0.0;
         for (int k = v.col_ptr[j]; k < v.col_ptr[j + 1]; ++k) {
-            double t = fabs(v.vals[(int64_t)v.csc_src[k] * B + mp.s] * v.dr[(int64_t)v.row_idx[k] * B + mp.s] * dcj);
+            const double val = v.vals[(int64_t)v.csc_src[k] * B + mp.s];
+            double t = fabs(val * v.dr[(int64_t)v.row_idx[k] * B + mp.s] * dcj);
             a = SUM ? a + t : fmax(a, t);
+            a0 = fmax(a0, fabs(val));
         }
-        v.scf[j * B + mp.s] = a > 0.0 ? 1.0 / sqrt(a) : 1.0;
+        v.scf[j * B + mp.s] = (a > 0.0 && a0 > tiny) ? 1.0 / sqrt(a) : 1.0;
     }
 }
 __global__ void k_mul_inplace(double *__restrict__ a, const double *__restrict__ b, int64_t n) {
@@ -740,7 +763,7 @@ class LpSolver {
     DBuf<double> vals, c, lb, ub, rl, ru, c0;
     DBuf<double> A, AT, dr, dc, sr, scf, cs, lbs, ubs, rls, rus;
     DBuf<double> x, xa, xp, xbar, gy, gyp, y, ya, yp, ray;
-    DBuf<double> xo, yo, dlo, dup, partials;
+    DBuf<double> xo, yo, dlo, dup, partials, gmax;
     DBuf<ScenState> state;
     DBuf<DevParams> prm;
     DBuf<int> n_active, kstep;
@@ -828,6 +851,7 @@ class LpSolver {
         ASM_TRY(AT.alloc(zB));
         ASM_TRY(c0.alloc(B));
         ASM_TRY(partials.alloc((size_t)Q_COUNT * kMaxBlocksX * B));
+        ASM_TRY(gmax.alloc(B));
         ASM_TRY(state.alloc(B));
         ASM_TRY(prm.alloc(1));
         ASM_TRY(n_active.alloc(1));
@@ -887,6 +911,7 @@ class LpSolver {
         v.dlo = dlo.p;
         v.dup = dup.p;
         v.partials = partials.p;
+        v.gmax = gmax.p;
         v.state = state.p;
         v.prm = prm.p;
         v.n_active = n_active.p;
@@ -903,6 +928,11 @@ class LpSolver {
         const int64_t nB = (int64_t)n * B, mB = (int64_t)m * B;
         ASM_KL(k_fill<<<ew_grid(mB), 1024, 0, stream>>>(dr.p, 1.0, mB));
         ASM_KL(k_fill<<<ew_grid(nB), 1024, 0, stream>>>(dc.p, 1.0, nB));
+        {
+            const Geo gz = geo_for(std::max<int64_t>(nnz, 1), B);
+            ASM_KB(k_absmax, gz, v, nnz);
+            ASM_KL(k_final_max<<<B, kFinalThreads, 0, stream>>>(partials.p, (int)gz.grid.x, B, gmax.p));
+        }
         for (int it = 0; it <= ruiz_iters; ++it) {
             if (it == ruiz_iters) {  // last pass: Pock-Chambolle (alpha = 1): 1-norms
                 ASM_KB2(k_ruiz_rows, true, gr, v);

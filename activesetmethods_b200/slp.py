@@ -160,10 +160,12 @@ class _Slp:
         pr, o = self.problem, self.options
         factory = o.external_optimizer
         if factory == "B200LP":
-            # like GLPK, which keeps its basis between the sub-LPs of a run (one glp_prob per SLP run, slp.jl:24),
-            # the engine starts every solve from the previous one's (p, lambda) unless told otherwise
+            # every sub-LP is solved from a cold start by default.  ``lp_options={"warm_start": 1}`` starts from the
+            # previous sub-LP's (p, lambda) -- the analogue of GLPK keeping its basis (one glp_prob per SLP run,
+            # slp.jl:24); it halves the PDHG work of line-search runs (case118: 1.03 M -> 0.51 M iterations) but is
+            # not yet robust on trust-region runs that sit in feasibility restoration, so it is opt-in
             return SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, batch=1, device=o.device,
-                         **{"warm_start": 1, **o.lp_options})
+                         **o.lp_options)
         return factory(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U)
 
     # slp.jl:23-47

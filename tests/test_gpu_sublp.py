@@ -83,6 +83,25 @@ def test_sublp_parity_live(gpu, name, alg, limit):
     lp.close()
 
 
+def test_numerically_empty_rows_do_not_stall(gpu):
+    """Regression (tests/golden/sublp_case118_tinyrow.npz): an SLP iterate whose thermal-limit rows have gradients
+    of ~3e-11.  Equilibrating those rows used to scale their right-hand sides by 2e10 and the solve ran into the
+    iteration limit; they are now treated as empty rows.  Status and objective against the oracle's simplex."""
+    from activesetmethods_b200.sublp import SubLp
+    g = np.load(os.path.join(GOLDEN, "sublp_case118_tinyrow.npz"))
+    pr = problem("case118")
+    pat = so.JacobianPattern(pr.m, pr.n, pr.j_str)
+    rowmax = np.asarray(abs(pat.matrix(pat.assemble(g["dE"]))).max(axis=1).todense()).ravel()
+    assert np.any((rowmax > 0) & (rowmax < 1e-9))            # the fixture really has such rows
+    lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, eps_rel=1e-7, max_iter=400000)
+    out = lp.sub_optimize(g["x"], float(g["f"]), g["df"], g["E"], g["dE"], float(g["delta"]), bool(g["fr"]))
+    info = lp.last_info[0]
+    assert out[5] == int(g["status"]) == 0, info
+    assert abs(info["objective"] - float(g["objective"])) <= OBJ_RTOL * abs(float(g["objective"]))
+    assert info["iterations"] < 200000, info
+    lp.close()
+
+
 def test_assembly_bit_exact_with_duplicates(gpu):
     """common.jl:12-20 with duplicate COO entries, wide dynamic range, signed zeros; batch of 40 scenarios."""
     from activesetmethods_b200.examples import small_nlps

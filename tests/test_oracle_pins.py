@@ -73,6 +73,18 @@ def test_golden_sublps_reproduce(name):
             assert abs(sub.last_objective - g["objective"][k]) <= 1e-9 * max(1.0, abs(g["objective"][k]))
 
 
+def test_golden_tinyrow_fixture_reproduces():
+    """tests/golden/sublp_case118_tinyrow.npz (recorded on the GPU SLP path) is what the oracle computes today."""
+    from helpers import problem
+    g = np.load(os.path.join(GOLDEN, "sublp_case118_tinyrow.npz"))
+    pr = problem("case118")
+    pat = so.JacobianPattern(pr.m, pr.n, pr.j_str)
+    sub = so.SubLp(pat, pr.g_L, pr.g_U, pr.x_L, pr.x_U)
+    out = sub.solve(pat.assemble(g["dE"]), g["df"], float(g["f"]), g["E"], g["x"], float(g["delta"]), bool(g["fr"]))
+    assert out[5] == int(g["status"]) == so.OPTIMAL
+    assert abs(sub.last_objective - float(g["objective"])) <= 1e-9 * abs(float(g["objective"]))
+
+
 def test_assemble_matches_literal_loop():
     """JacobianPattern.assemble == the scalar J[r,c] += v loop of common.jl:15-18, bit for bit, with duplicates."""
     rng = np.random.default_rng(7)
