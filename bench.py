@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "sub-LP scenarios/s (SLP hot path: assembly + bounds + LP solve to 1e-6 + read-back + merit)"
+METRIC = "sub-LP scenarios/s (SLP hot path: assembly + bounds + LP solve to 1e-6 objective accuracy + read-back + merit)"
 UNIT = "scenarios/s"
 
 
@@ -339,7 +339,8 @@ def run_ours(a):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
-                "kernel": "k_primal<batch> + k_dual<batch> (one PDHG iteration of the whole batch)",
+                "kernel": "k_primal2 + k_dual2 (one PDHG iteration of the whole batch; k_primal/k_dual<batch> "
+                          "when the padded batch is not a multiple of 64)",
                 "bytes_per_launch_pair": by_primal + by_dual, "primal_ms": pm, "dual_ms": dm,
                 "primal_gbs": by_primal / (pm * 1e-3) / 1e9, "dual_gbs": by_dual / (dm * 1e-3) / 1e9,
                 "loop_ms_per_iteration": loop_ms / max(loop_its, 1)}
