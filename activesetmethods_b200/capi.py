@@ -89,6 +89,8 @@ SIGNATURES = {
     "asm_slp_merit_derivative": (C.c_int, [_VP, c_double_p, C.c_int32, c_double_p]),
     "asm_slp_launch_count": (C.c_int64, [_VP]),
     "asm_slp_last_solve_timing": (C.c_int, [_VP, c_double_p, c_int64_p]),
+    "asm_plan_check": (C.c_int, [C.c_int32, C.c_int32, c_int64_p, c_int32_p, C.c_int32, c_int64_p, c_int32_p,
+                                 c_int64_p]),
     "asm_slp_engine_info": (C.c_int, [_VP, c_int32_p, c_int32_p, c_int32_p]),
     "asm_slp_reassemble": (C.c_int, [_VP, C.c_int32]),
     "asm_slp_extract_device": (C.c_int, [_VP]),

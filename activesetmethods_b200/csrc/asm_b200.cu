@@ -1137,6 +1137,89 @@ int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations) 
     return ASM_OK;
 }
 
+// Host-only self-check of the group engine's layout (no device needed): builds the sliced-ELL / halo layout of a
+// CSR pattern for groups of G blocks, rebuilds every row from it and compares with the input.
+int asm_plan_check(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, int32_t G,
+                   int64_t *smem_bytes, int32_t *matrix_resident, int64_t *padded_entries) {
+    if (!row_ptr || n_cols <= 0 || n_rows < 0 || G < 1) return fail(ASM_E_INVALID, "bad argument");
+    const int64_t nnz = row_ptr[n_rows];
+    if (nnz > 0 && !col_idx) return fail(ASM_E_INVALID, "null col_idx");
+    std::vector<int> rp(n_rows + 1), ci(nnz);
+    for (int i = 0; i <= n_rows; ++i) rp[i] = (int)row_ptr[i];
+    for (int64_t k = 0; k < nnz; ++k) {
+        if (col_idx[k] < 0 || col_idx[k] >= n_cols) return fail(ASM_E_INVALID, "column index out of range");
+        ci[k] = col_idx[k];
+    }
+    SellSide R;
+    build_sell_side(n_rows, n_cols, rp.data(), ci.data(), nullptr, G, R);
+    if ((int)R.first.size() != G) return fail(ASM_E_STATE, "wrong number of blocks");
+    std::vector<char> seen(nnz, 0);
+    int64_t rows_seen = 0, padded = 0;
+    int next_first = 0;
+    for (int c = 0; c < G; ++c) {
+        if (R.first[c] != next_first) return fail(ASM_E_STATE, "row ranges are not contiguous");
+        next_first += R.cnt[c];
+        const int *ptr = R.ptr.data() + R.ptr_base[c];
+        const int *halo = R.halo.data() + R.halo_base[c];
+        for (int t = 1; t < R.halo_cnt[c]; ++t)
+            if (halo[t - 1] >= halo[t]) return fail(ASM_E_STATE, "halo list is not strictly increasing");
+        for (int q = 0; q < R.nslice[c]; ++q) {
+            const int len = ptr[q + 1] - ptr[q];
+            for (int lane = 0; lane < 32; ++lane) {
+                const int sl = R.slot_base[c] + q * 32 + lane;
+                const int row = R.slot[sl], tail = R.tail[sl];
+                if (lane + tail > 31) return fail(ASM_E_STATE, "row group crosses a slice");
+                if (row >= 0) {
+                    if (row < R.first[c] || row >= R.first[c] + R.cnt[c]) return fail(ASM_E_STATE, "row outside its block");
+                    ++rows_seen;
+                    // entries of the head lane and of its `tail` followers, in lane order, must be the CSR row
+                    int64_t k = rp[row];
+                    for (int g = 0; g <= tail; ++g)
+                        for (int e = 0; e < len; ++e) {
+                            const size_t at = (size_t)R.base[c] + ((size_t)ptr[q] + e) * 32 + lane + g;
+                            const int src = R.src[at];
+                            if (src < 0) continue;
+                            if (src != k || seen[src]) return fail(ASM_E_STATE, "sliced-ELL entry out of order");
+                            if (R.idx[at] < 0 || R.idx[at] >= R.halo_cnt[c] || halo[R.idx[at]] != ci[src])
+                                return fail(ASM_E_STATE, "halo position does not map back to the column");
+                            seen[src] = 1;
+                            ++k;
+                        }
+                    if (k != rp[row + 1]) return fail(ASM_E_STATE, "row incomplete in the sliced-ELL layout");
+                }
+            }
+            padded += (int64_t)len * 32;
+        }
+    }
+    if (next_first != n_rows || rows_seen != n_rows) return fail(ASM_E_STATE, "rows lost by the partition");
+    for (int64_t k = 0; k < nnz; ++k)
+        if (!seen[k]) return fail(ASM_E_STATE, "matrix entry missing from the layout");
+    // shared-memory need of the full (two-sided) plan
+    std::vector<int> cp(n_cols + 1, 0), ri(nnz);
+    for (int64_t k = 0; k < nnz; ++k) cp[ci[k] + 1]++;
+    for (int j = 0; j < n_cols; ++j) cp[j + 1] += cp[j];
+    {
+        std::vector<int> cur(cp.begin(), cp.end() - 1);
+        for (int i = 0; i < n_rows; ++i)
+            for (int k = rp[i]; k < rp[i + 1]; ++k) ri[cur[ci[k]]++] = i;
+    }
+    LpSolver tmp;
+    tmp.n = n_cols;
+    tmp.m = n_rows;
+    tmp.nnz = nnz;
+    tmp.h_row_ptr = rp;
+    tmp.h_col_idx = ci;
+    tmp.h_col_ptr = cp;
+    tmp.h_row_idx = ri;
+    SellSide R2, C2;
+    GroupSmem sm;
+    const size_t bytes = LpSolver::plan_layout(tmp, G, R2, C2, sm);
+    if (smem_bytes) *smem_bytes = (int64_t)bytes;
+    if (matrix_resident) *matrix_resident = sm.mats;
+    if (padded_entries) *padded_entries = padded;
+    return ASM_OK;
+}
+
 int asm_slp_engine_info(asm_slp *h, int32_t *engine, int32_t *group_size, int32_t *groups) {
     if (!h) return fail(ASM_E_INVALID, "null handle");
     if (!h->h.solved) return fail(ASM_E_STATE, "no solve yet");

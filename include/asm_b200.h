@@ -199,6 +199,11 @@ int64_t asm_slp_launch_count(asm_slp *h);
  * the total PDHG iterations it ran (max over the batch) */
 int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations);
 
+/* host-only self-check of the group engine's data layout for groups of G blocks (no device needed): rebuilds
+ * every row of the pattern from the sliced-ELL / halo arrays; returns the dynamic shared memory one block needs,
+ * whether the matrix values stay resident there, and the padded entry count of the row side */
+int asm_plan_check(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, int32_t G,
+                   int64_t *smem_bytes, int32_t *matrix_resident, int64_t *padded_entries);
 /* which engine the last asm_slp_solve used (1 streaming, 2 group), blocks per LP and LPs resident at once */
 int asm_slp_engine_info(asm_slp *h, int32_t *engine, int32_t *group_size, int32_t *groups);
 
