@@ -17,6 +17,8 @@
 // A solve launches a CUDA graph of `check_every` iterations per host round trip; the only host<->device
 // traffic inside the loop is the 4-byte active counter.
 #pragma once
+#include <chrono>
+#include <cstdlib>
 #include <map>
 #include <memory>
 
@@ -722,6 +724,38 @@ __global__ void __launch_bounds__(kThreads) k_finalize(LpView v) {
 #include "pdhg_group.cuh"
 namespace asmb {
 
+// ---- live-set compaction of a streaming batch ------------------------------------------------------------------
+// dst[i * Bd + t] = src[i * Bs + map[t]] (t < cnt; padding lanes copy map[0]) and the reverse scatter
+__global__ void k_gather_cols(const double *__restrict__ src, double *__restrict__ dst, int64_t rows, int Bs, int Bd,
+                              const int *__restrict__ map, int cnt) {
+    const int64_t total = rows * Bd;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / Bd;
+        const int t = (int)(e - i * Bd);
+        dst[e] = src[i * Bs + map[t < cnt ? t : 0]];
+    }
+}
+__global__ void k_scatter_cols(const double *__restrict__ src, double *__restrict__ dst, int64_t rows, int Bs, int Bd,
+                               const int *__restrict__ map, int cnt) {
+    const int64_t total = rows * cnt;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / cnt;
+        const int t = (int)(e - i * cnt);
+        dst[i * Bd + map[t]] = src[i * Bs + t];
+    }
+}
+__global__ void k_gather_state(const ScenState *src, ScenState *dst, const int *map, int cnt, int Bd) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Bd) return;
+    ScenState st = src[map[t < cnt ? t : 0]];
+    if (t >= cnt) st.status = ASM_LP_OPTIMAL;  // padding lane: never live
+    dst[t] = st;
+}
+__global__ void k_scatter_state(const ScenState *src, ScenState *dst, const int *map, int cnt) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < cnt) dst[map[t]] = src[t];
+}
+
 // ================================================================================================================
 #define ASM_KL(...)      \
     do {                 \
@@ -758,6 +792,19 @@ class LpSolver {
     std::map<int, std::unique_ptr<GroupPlan>> plans;  // persistent group engine (pdhg_group.cuh), by group size
     std::map<int, std::pair<size_t, int>> feas;       // group size -> (shared memory bytes, matrix resident)
     GroupPlan *plan = nullptr;
+    // live-set compaction (streaming engine): when half of the batch has converged the running LPs are copied
+    // into a narrower working set so that no bandwidth is spent on finished ones
+    struct WorkSet {
+        DBuf<double> A, AT, cs, lbs, ubs, rls, rus, x, xa, xp, xbar, gy, gyp, y, ya, yp, ray, dr, dc, lb, ub, xo, yo, dlo, dup;
+        DBuf<ScenState> state;
+        DBuf<int> orig;
+        std::vector<int> h_orig;  // position in the home batch
+        int cap = 0, B = 0, live = 0;
+    };
+    WorkSet wsets[2];
+    WorkSet *cur = nullptr;  // active compact set (nullptr: the home arrays)
+    int homeB = 0, homeBuser = 0;
+    int compactions = 0;
     int last_engine = 0, last_G = 0, last_groups = 0;
     // data (unscaled, element-major)
     DBuf<double> vals, c, lb, ub, rl, ru, c0;
@@ -915,7 +962,103 @@ class LpSolver {
         v.state = state.p;
         v.prm = prm.p;
         v.n_active = n_active.p;
+        if (cur) {
+            WorkSet &w = *cur;
+            v.A = w.A.p; v.AT = w.AT.p; v.cs = w.cs.p; v.lbs = w.lbs.p; v.ubs = w.ubs.p; v.rls = w.rls.p; v.rus = w.rus.p;
+            v.x = w.x.p; v.xa = w.xa.p; v.xp = w.xp.p; v.xbar = w.xbar.p; v.gy = w.gy.p; v.gyp = w.gyp.p;
+            v.y = w.y.p; v.ya = w.ya.p; v.yp = w.yp.p; v.ray = w.ray.p; v.dr = w.dr.p; v.dc = w.dc.p;
+            v.lb = w.lb.p; v.ub = w.ub.p; v.xo = w.xo.p; v.yo = w.yo.p; v.dlo = w.dlo.p; v.dup = w.dup.p;
+            v.state = w.state.p;
+        }
         return v;
+    }
+
+    int alloc_workset(WorkSet &w, int capB) {
+        if (w.cap >= capB) return ASM_OK;
+        const size_t nB = (size_t)n * capB, mB = (size_t)std::max(m, 1) * capB, zB = (size_t)std::max<int64_t>(nnz, 1) * capB;
+        DBuf<double> *zz[] = {&w.A, &w.AT};
+        for (auto *b : zz) ASM_TRY(b->alloc(zB));
+        DBuf<double> *nn[] = {&w.cs, &w.lbs, &w.ubs, &w.x, &w.xa, &w.xp, &w.xbar, &w.gy, &w.gyp, &w.dc, &w.lb, &w.ub, &w.xo, &w.dlo, &w.dup};
+        for (auto *b : nn) ASM_TRY(b->alloc(nB));
+        DBuf<double> *mm[] = {&w.rls, &w.rus, &w.y, &w.ya, &w.yp, &w.ray, &w.dr, &w.yo};
+        for (auto *b : mm) ASM_TRY(b->alloc(mB));
+        ASM_TRY(w.state.alloc(capB));
+        ASM_TRY(w.orig.alloc(capB));
+        w.cap = capB;
+        return ASM_OK;
+    }
+
+    // outputs and states of the active compact set back to their home positions
+    int scatter_home() {
+        if (!cur) return ASM_OK;
+        WorkSet &w = *cur;
+        const int cnt = w.live;
+        auto sc = [&](const DBuf<double> &src, DBuf<double> &dst, int64_t rows) {
+            if (rows == 0 || cnt == 0) return;
+            k_scatter_cols<<<ew_grid(rows * cnt), 1024, 0, stream>>>(src.p, dst.p, rows, w.B, homeB, w.orig.p, cnt);
+            ++launches;
+        };
+        sc(w.xo, xo, n);
+        sc(w.dlo, dlo, n);
+        sc(w.dup, dup, n);
+        sc(w.yo, yo, m);
+        if (cnt) {
+            k_scatter_state<<<(cnt + 127) / 128, 128, 0, stream>>>(w.state.p, state.p, w.orig.p, cnt);
+            ++launches;
+        }
+        ASM_CK(cudaGetLastError());
+        return ASM_OK;
+    }
+
+    // copy the running LPs of the current set into a narrower one; host_state must hold the current states
+    int compact() {
+        LpView v = view();
+        const Geo gm = geo_for(std::max(n, m), B);
+        ASM_KB(k_finalize, gm, v);   // finished LPs get their final outputs now
+        ASM_TRY(scatter_home());
+        std::vector<int> src, orig;
+        for (int s2 = 0; s2 < Buser; ++s2)
+            if (host_state[s2].status < 0) {
+                src.push_back(s2);
+                orig.push_back(cur ? cur->h_orig[s2] : s2);
+            }
+        const int cnt = (int)src.size();
+        if (cnt == 0) return ASM_OK;
+        const int Bn = pad_batch(cnt);
+        WorkSet &w = (cur == &wsets[0]) ? wsets[1] : wsets[0];
+        ASM_TRY(alloc_workset(w, Bn));
+        DBuf<int> dsrc;
+        ASM_TRY(dsrc.alloc(cnt));
+        ASM_CK(cudaMemcpyAsync(dsrc.p, src.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, stream));
+        ASM_CK(cudaMemcpyAsync(w.orig.p, orig.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice, stream));
+        auto ga = [&](const double *from, DBuf<double> &to, int64_t rows) {
+            if (rows == 0) return;
+            k_gather_cols<<<ew_grid(rows * Bn), 1024, 0, stream>>>(from, to.p, rows, B, Bn, dsrc.p, cnt);
+            ++launches;
+        };
+        ga(v.A, w.A, nnz); ga(v.AT, w.AT, nnz);
+        ga(v.cs, w.cs, n); ga(v.lbs, w.lbs, n); ga(v.ubs, w.ubs, n); ga(v.x, w.x, n); ga(v.xa, w.xa, n); ga(v.dc, w.dc, n);
+        ga(v.lb, w.lb, n); ga(v.ub, w.ub, n);
+        ga(v.rls, w.rls, m); ga(v.rus, w.rus, m); ga(v.y, w.y, m); ga(v.ya, w.ya, m); ga(v.dr, w.dr, m);
+        // the last checked point travels too: an LP that hits the iteration limit reports it
+        ga(v.xp, w.xp, n); ga(v.gyp, w.gyp, n); ga(v.yp, w.yp, m);
+        k_gather_state<<<(Bn + 127) / 128, 128, 0, stream>>>(v.state, w.state.p, dsrc.p, cnt, Bn);
+        ++launches;
+        ASM_CK(cudaGetLastError());
+        ASM_CK(cudaMemcpyAsync(n_active.p, &cnt, sizeof(int), cudaMemcpyHostToDevice, stream));
+        ASM_CK(cudaStreamSynchronize(stream));   // dsrc / src / cnt go out of scope
+        w.h_orig = orig;
+        w.B = Bn;
+        w.live = cnt;
+        cur = &w;
+        B = Bn;
+        Buser = cnt;
+        if (graph_exec) {
+            cudaGraphExecDestroy(graph_exec);
+            graph_exec = nullptr;
+        }
+        ++compactions;
+        return ASM_OK;
     }
 
     static unsigned ew_grid(int64_t cnt) {
@@ -1353,6 +1496,14 @@ class LpSolver {
         //         2 = persistent on-chip group kernel, 0 = group kernel when the LP fits, else streaming
         // engine 0: a single LP runs on the group kernel; a batch streams until a quarter of it is left, then the
         // stragglers finish on the group kernel, each to its own convergence
+        if (cur) {   // a previous solve failed half way: back to the home batch
+            cur = nullptr;
+            B = homeB;
+            Buser = homeBuser;
+        }
+        homeB = B;
+        homeBuser = Buser;
+        compactions = 0;
         const int hand_over = Buser == 1 ? 0 : std::max(1, std::min(Buser, (int)(P.hand_over * Buser)));
         const bool plan_ok = P.engine != 1 && ensure_plan(P.group_size, P.engine == 2 ? Buser : std::max(1, hand_over)) == ASM_OK;
         if (P.engine == 2 && !plan_ok) return ensure_plan(P.group_size, Buser);
@@ -1363,37 +1514,89 @@ class LpSolver {
         last_groups = 0;
         int live = Buser;
         bool limit = false;
+        const bool trace = getenv("ASM_TRACE") != nullptr;
+        auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_phase = now();
         if (!group_only) {
-            ASM_TRY(build_graph(steps));
+            // cost model (seconds per iteration of one running LP), calibrated on B200 (profiles/): the streaming
+            // kernels move the whole working set at ~4.4 TB/s plus two launches; the group kernel costs
+            // (sync + work / G) on G of the machine's SMs
+            int n_sms = kSMs;
+            cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, 0);
+            const double bytes_it = 16.0 * (double)nnz + 64.0 * n + 48.0 * m;
+            auto stream_cost = [&](int Bc, int lv) { return ((double)Bc * bytes_it / 4.4e12 + 8e-6) / std::max(1, lv); };
+            auto group_cost = [&](int lv) {
+                const int G = choose_group(P.group_size, lv, n_sms);
+                if (G < 0) return 1e30;
+                const double t = ((G <= kMaxClusterG ? 2.8 : 4.4) + 1.5e-3 * (double)nnz / G) * 1e-6;
+                const int resident = std::max(1, (int)(0.8 * n_sms) / G);
+                return t / std::min(lv, resident);
+            };
             int64_t it = 0;
             while (it < P.max_iter) {
+                ASM_TRY(build_graph(steps));
                 ASM_CK(cudaGraphLaunch(graph_exec, stream));
                 launches += launches_per_graph;
                 it += steps;
                 ASM_CK(cudaMemcpyAsync(flag, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
                 ASM_CK(cudaStreamSynchronize(stream));
-                if (*flag <= (plan_ok ? hand_over : 0)) break;
+                live = *flag;
+                if (live <= 0) break;
+                const bool shrink = P.engine == 0 && B >= 128 && pad_batch(live) * 2 <= B;
+                if (plan_ok && live <= hand_over && group_cost(live) < stream_cost(shrink ? pad_batch(live) : B, live)) break;
+                if (shrink) {
+                    LpView vv = view();
+                    ASM_CK(cudaMemcpyAsync(host_state.data(), vv.state, sizeof(ScenState) * B, cudaMemcpyDeviceToHost, stream));
+                    ASM_CK(cudaStreamSynchronize(stream));
+                    const int before = B;
+                    ASM_TRY(compact());
+                    if (trace)
+                        fprintf(stderr, "[asm] it %lld: %d LPs running, batch %d -> %d (%.3f s since last event)\n",
+                                (long long)it, live, before, B, now() - t_phase);
+                    t_phase = now();
+                }
             }
-            live = *flag;
             limit = it >= P.max_iter;
             last_engine |= 1;
         }
         // group phase: re-planned as the live set thins out (wider groups for the last stragglers)
+        if (trace && !group_only)
+            fprintf(stderr, "[asm] streaming phase done: %d LPs still running (%.3f s since last event)\n", live, now() - t_phase);
+        t_phase = now();
         while (plan_ok && live > 0 && !limit) {
             ASM_TRY(ensure_plan(P.group_size, live));
             const long long budget = live > 1 ? (1LL << 16) : P.max_iter;
             ASM_TRY(run_group(P, steps, live, budget));
             last_engine |= 2;
-            ASM_CK(cudaMemcpyAsync(host_state.data(), state.p, sizeof(ScenState) * B, cudaMemcpyDeviceToHost, stream));
+            LpView vv = view();
+            ASM_CK(cudaMemcpyAsync(host_state.data(), vv.state, sizeof(ScenState) * B, cudaMemcpyDeviceToHost, stream));
             ASM_CK(cudaStreamSynchronize(stream));
+            if (trace) {
+                fprintf(stderr, "[asm] group launch: %d LPs, G = %d (%s, matrix %s), %d groups resident, %.3f s\n", live,
+                        plan->G, plan->cluster ? "cluster" : "grid", plan->sm.mats ? "resident" : "streamed", plan->n_groups,
+                        now() - t_phase);
+                t_phase = now();
+            }
             live = 0;
             for (int s = 0; s < Buser; ++s)
                 if (host_state[s].status < 0 && host_state[s].total < P.max_iter) ++live;
         }
         ASM_CK(cudaEventRecord(ev1, stream));
-        LpView v = view();
-        const Geo gm = geo_for(std::max(n, m), B);
-        ASM_KB(k_finalize, gm, v);
+        {
+            LpView v = view();
+            const Geo gm = geo_for(std::max(n, m), B);
+            ASM_KB(k_finalize, gm, v);
+        }
+        if (cur) {   // back to the home batch
+            ASM_TRY(scatter_home());
+            cur = nullptr;
+            B = homeB;
+            Buser = homeBuser;
+            if (graph_exec) {
+                cudaGraphExecDestroy(graph_exec);
+                graph_exec = nullptr;
+            }
+        }
         ASM_CK(cudaMemcpyAsync(host_state.data(), state.p, sizeof(ScenState) * B, cudaMemcpyDeviceToHost, stream));
         std::vector<double> hc0(B, 0.0);
         ASM_CK(cudaMemcpyAsync(hc0.data(), c0.p, sizeof(double) * B, cudaMemcpyDeviceToHost, stream));
