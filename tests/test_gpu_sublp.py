@@ -174,6 +174,41 @@ def test_batch_matches_single(gpu):
     lpb.close()
 
 
+def test_large_batch_with_compaction(gpu):
+    """160 perturbed case9 scenarios: wide enough (>= 128) for the streaming engine to compact the running LPs into
+    a narrower working set as they converge and to hand the stragglers to the group kernel.  Every scenario must
+    come back in its own slot: objective against the oracle for scenarios spread over the batch, all optimal, primal
+    steps feasible for their own (per-scenario) bounds."""
+    from activesetmethods_b200.examples import acopf
+    from activesetmethods_b200.sublp import SubLp
+    net = acopf.case9()
+    B = 160
+    mdls = [acopf.AcopfModel(acopf.perturb_loads(net, s + 1)) for s in range(B)]
+    m0 = mdls[0]
+    gL = np.array([m.g_L for m in mdls]); gU = np.array([m.g_U for m in mdls])
+    xL = np.array([m.x_L for m in mdls]); xU = np.array([m.x_U for m in mdls])
+    x = np.array([np.clip(m.x0, m.x_L, m.x_U) for m in mdls])
+    f = np.array([m.eval_f(xx) for m, xx in zip(mdls, x)])
+    df = np.array([m.eval_grad_f(xx, np.zeros(m.n)) for m, xx in zip(mdls, x)])
+    E = np.array([m.eval_g(xx, np.zeros(m.m)) for m, xx in zip(mdls, x)])
+    dE = np.array([m.eval_jac_g(xx, "eval", None, None, np.zeros(m.nnz)) for m, xx in zip(mdls, x)])
+    lpb = SubLp(m0.n, m0.m, m0.j_str, xL, xU, gL, gU, batch=B, eps_rel=1e-7)
+    pb, lamb, _, _, _, stb = lpb.sub_optimize(x, f, df, E, dE, 1000.0, False)
+    assert np.all(stb == 0)
+    objs = np.array([i["objective"] for i in lpb.last_info])
+    its = np.array([i["iterations"] for i in lpb.last_info])
+    assert its.max() > 2 * np.median(its) or its.min() < its.max()      # they do not all stop together
+    pat = so.JacobianPattern(m0.m, m0.n, m0.j_str)
+    for s in (0, 1, 63, 64, 77, 128, 159):
+        ref = so.SubLp(pat, gL[s], gU[s], xL[s], xU[s])
+        ref.solve(pat.assemble(dE[s]), df[s], f[s], E[s], x[s], 1000.0, False)
+        assert abs(objs[s] - ref.last_objective) <= OBJ_RTOL * max(1.0, abs(ref.last_objective)), (s, objs[s])
+        K, cost, off, lb, ub, rl, ru = ref.last_lp
+        xfull = np.zeros(K.shape[1]); xfull[:m0.n] = pb[s]
+        assert lp_feasibility(K, xfull, lb, ub, rl, ru) <= FEAS_TOL, s
+    lpb.close()
+
+
 def test_generic_lp_against_highs(gpu):
     """B200LP as a general external LP optimizer: random feasible bounded LPs against HiGHS."""
     import scipy.sparse as sp
