@@ -309,6 +309,7 @@ class DistLp {
         dp.kp = P.pid_kp;
         dp.ki = P.pid_ki;
         dp.kd = P.pid_kd;
+        dp.balance = P.weight_balance;
         dp.verbose = P.verbose && rank == 0;
         ASM_CK(cudaMemcpyAsync(L.prm.p, &dp, sizeof dp, cudaMemcpyHostToDevice, stream));
         ASM_CK(cudaStreamSynchronize(stream));

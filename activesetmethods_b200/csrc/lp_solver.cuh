@@ -42,6 +42,7 @@ struct DevParams {
     double eps_rel, eps_infeas;
     double b_suf, b_nec, b_art;
     double kp, ki, kd;
+    double balance;
     int verbose;
 };
 
@@ -618,7 +619,12 @@ __global__ void __launch_bounds__(kFinalThreads) k_decide(LpView v, int jit, int
             // PDLP rule omega <- sqrt(omega * |dy| / |dx|).  Degenerate moves or a runaway weight fall back to
             // the initial one.
             const double ddx = sqrt(q[Q_DXA2]), ddy = sqrt(q[Q_DYA2]);
-            if (ddx > 1e-16 && ddy > 1e-16) {
+            const double rp = pres / (1.0 + st.nq_un), rd = dres / (1.0 + st.nc_un);
+            if (P.balance > 0.0) {
+                // residual balancing: a larger weight shortens the primal step and lengthens the dual one, which
+                // drives the primal residual down faster -- move the weight towards equal relative residuals
+                if (rp > 0.0 && rd > 0.0) st.omega = exp(log(st.omega) + P.balance * log(rp / rd));
+            } else if (ddx > 1e-16 && ddy > 1e-16) {
                 const double e = log(st.omega * ddx / ddy);
                 st.e_sum += e;
                 const double dlog = -(P.kp * e + P.ki * st.e_sum + P.kd * (e - st.e_prev));
@@ -1479,10 +1485,11 @@ class LpSolver {
         dp.kp = P.pid_kp;
         dp.ki = P.pid_ki;
         dp.kd = P.pid_kd;
+        dp.balance = P.weight_balance;
         dp.verbose = P.verbose;
         int *flag = (int *)pin_flag.p;
         DevParams *pdp = (DevParams *)((char *)pin_flag.p + 16);
-        static_assert(sizeof(DevParams) + 16 <= 128, "pinned flag area too small");
+        static_assert(sizeof(DevParams) + 16 <= 128, "pinned flag area too small");  // 9 doubles + int
         ASM_TRY(pin_flag.reserve(128));
         flag = (int *)pin_flag.p;
         pdp = (DevParams *)((char *)pin_flag.p + 16);

@@ -303,7 +303,12 @@ __device__ inline void group_decide(ScenState &st, const DevParams &P, const dou
         st.r_prev = r;
         if (restart) {
             const double ddx = sqrt(q[Q_DXA2]), ddy = sqrt(q[Q_DYA2]);
-            if (ddx > 1e-16 && ddy > 1e-16) {
+            const double rp = pres / (1.0 + st.nq_un), rd = dres / (1.0 + st.nc_un);
+            if (P.balance > 0.0) {
+                // residual balancing: a larger weight shortens the primal step and lengthens the dual one, which
+                // drives the primal residual down faster -- move the weight towards equal relative residuals
+                if (rp > 0.0 && rd > 0.0) st.omega = exp(log(st.omega) + P.balance * log(rp / rd));
+            } else if (ddx > 1e-16 && ddy > 1e-16) {
                 const double e = log(st.omega * ddx / ddy);
                 st.e_sum += e;
                 const double dlog = -(P.kp * e + P.ki * st.e_sum + P.kd * (e - st.e_prev));

@@ -69,7 +69,9 @@ typedef struct asm_lp_params {
     int32_t group_size;    /* blocks per LP for engine 2 (0 = auto)                                          */
     double hand_over;      /* engine 0 on a batch: fraction of the batch still running at which the          */
                            /* streaming kernels hand the stragglers to the group kernel (default 0.5)        */
-    double reserved[2];
+    double weight_balance; /* > 0: at restarts move the primal weight by (relative primal residual / relative dual  */
+                           /* residual)^weight_balance instead of the PDLP rule (0 = PDLP rule, the default)          */
+    double reserved[1];
 } asm_lp_params;
 void asm_lp_default_params(asm_lp_params *p);
 
