@@ -160,12 +160,14 @@ class _Slp:
         pr, o = self.problem, self.options
         factory = o.external_optimizer
         if factory == "B200LP":
-            # every sub-LP is solved from a cold start by default.  ``lp_options={"warm_start": 1}`` starts from the
-            # previous sub-LP's (p, lambda) -- the analogue of GLPK keeping its basis (one glp_prob per SLP run,
-            # slp.jl:24); it halves the PDHG work of line-search runs (case118: 1.03 M -> 0.51 M iterations) but is
-            # not yet robust on trust-region runs that sit in feasibility restoration, so it is opt-in
+            # Line search: every sub-LP starts from the previous one's (p, lambda) -- the analogue of GLPK keeping
+            # its basis (one glp_prob per SLP run, slp.jl:24); it halves the PDHG work (case118: 1.03 M -> 0.51 M
+            # iterations for the same 14 SLP iterations).  Trust region: cold starts; there a warm start changes
+            # which minimiser of the (degenerate) restoration LPs is returned and the runs measured so far ended
+            # further from the optimum.  ``lp_options={"warm_start": ...}`` overrides either.
+            warm = 1 if o.algorithm == "Line Search" else 0
             return SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, batch=1, device=o.device,
-                         **o.lp_options)
+                         **{"warm_start": warm, **o.lp_options})
         return factory(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U)
 
     # slp.jl:23-47
@@ -407,6 +409,14 @@ class SlpTR(_Slp):
                 if self.feasibility_restoration:
                     self.feasibility_restoration = False
                     self.iter += 1
+                    # Deviation from slp_trust_region.jl:163-170, which `continue`s here without ever reaching
+                    # its max_iter test: once the trust region has collapsed (delta ~ 1e-7) at a point that is
+                    # feasible to tolerance but whose linearisation is infeasible inside the tiny box, the
+                    # reference alternates normal LP (INFEASIBLE) / restoration LP forever.  Stop as its own
+                    # max_iter branch (:177-183) would.
+                    if self.iter >= o.max_iter:
+                        self.ret = 6 if self.prim_infeas <= o.tol_infeas else -1
+                        break
                     continue
                 elif self.dual_infeas <= o.tol_residual:
                     self.ret = 0

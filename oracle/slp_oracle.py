@@ -594,6 +594,9 @@ class SlpTR(_Slp):
                 if self.feasibility_restoration:
                     self.feasibility_restoration = False
                     self.iter += 1
+                    if self.iter >= o.max_iter:          # guard: the reference loops forever here (see slp.py)
+                        self.ret = 6 if self.prim_infeas <= o.tol_infeas else -1
+                        break
                     continue
                 elif self.dual_infeas <= o.tol_residual:
                     self.ret = 0
