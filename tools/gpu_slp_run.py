@@ -18,6 +18,15 @@ pr = problem(name)
 mdl = Model.from_problem(pr, Parameters(algorithm=alg, max_iter=max_iter, lp_options=opts))
 slp = (SlpLS if alg == "Line Search" else SlpTR)(mdl)
 t0 = time.time()
+
+
+def progress(s_, d):
+    if s_.lp_log:
+        print(f"  [{time.time() - t0:7.1f}s] SLP it {s_.iter} last LP {s_.lp_log[-1]} prim_infeas {s_.prim_infeas:.3e} "
+              f"f {s_.f:.6f} alpha {s_.alpha:.3g}", flush=True)
+
+
+slp.record = progress
 slp.run()
 dt = time.time() - t0
 its = [e[3] for e in slp.lp_log]
