@@ -29,7 +29,7 @@ class LpParams(C.Structure):
         ("restart_sufficient", C.c_double), ("restart_necessary", C.c_double), ("restart_artificial", C.c_double),
         ("pid_kp", C.c_double), ("pid_ki", C.c_double), ("pid_kd", C.c_double),
         ("engine", C.c_int32), ("group_size", C.c_int32),
-        ("hand_over", C.c_double), ("weight_balance", C.c_double), ("reserved", C.c_double * 1),
+        ("hand_over", C.c_double), ("weight_balance", C.c_double), ("tiny_rel", C.c_double),
     ]
 
 

@@ -254,7 +254,7 @@ class DistLp {
         {   // largest coefficient of the whole matrix (all ranks) and of every column
             const Geo gz = geo_for(std::max<int64_t>(L.nnz, 1), 1);
             ASM_KL(k_absmax<false><<<gz.grid, gz.block, 0, stream>>>(v, L.nnz));
-            ASM_KL(k_final_max<<<1, kFinalThreads, 0, stream>>>(L.partials.p, (int)gz.grid.x, 1, L.gmax.p));
+            ASM_KL(k_final_max<<<1, kFinalThreads, 0, stream>>>(L.partials.p, (int)gz.grid.x, 1, L.gmax.p, L.tiny_rel / kTinyRel));
             ASM_TRY(allreduce(L.gmax.p, L.gmax.p, 1, NcclApi::kMax));
             ASM_KL(k_col_norm_partial<false><<<gc.grid, gc.block, 0, stream>>>(v, t_part.p));
             ASM_TRY(allreduce(t_part.p + n, a0_full.p, n, NcclApi::kMax));
@@ -313,6 +313,7 @@ class DistLp {
         dp.verbose = P.verbose && rank == 0;
         ASM_CK(cudaMemcpyAsync(L.prm.p, &dp, sizeof dp, cudaMemcpyHostToDevice, stream));
         ASM_CK(cudaStreamSynchronize(stream));
+        L.tiny_rel = P.tiny_rel > 0.0 ? P.tiny_rel : kTinyRel;
         ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && L.has_solution) ? (int)P.warm_start : 0));
         const int steps = std::max(2, (int)P.check_every);
         LpView v = L.view();

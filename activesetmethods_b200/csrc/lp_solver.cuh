@@ -100,9 +100,11 @@ __global__ void __launch_bounds__(kThreads) k_absmax(LpView v, int64_t nnz) {
     for (int64_t k = mp.first; k < nnz; k += mp.stride) acc[0] = fmax(acc[0], fabs(v.vals[k * B + mp.s]));
     block_reduce_store<BATCH, 1>(acc, 1u, v.partials, 0, B);
 }
-__global__ void __launch_bounds__(kFinalThreads) k_final_max(const double *partials, int nbx, int B, double *out) {
+// out = matrix maximum times (tiny_rel / kTinyRel): the scaling kernels compare against kTinyRel * out
+__global__ void __launch_bounds__(kFinalThreads) k_final_max(const double *partials, int nbx, int B, double *out,
+                                                              double rel) {
     const double q = final_reduce(partials, 0, nbx, B, blockIdx.x, true);
-    if (threadIdx.x == 0) out[blockIdx.x] = q;
+    if (threadIdx.x == 0) out[blockIdx.x] = q * rel;
 }
 template <bool BATCH, bool SUM>
 __global__ void __launch_bounds__(kThreads) k_ruiz_rows(LpView v) {
@@ -1071,6 +1073,7 @@ class LpSolver {
         return (unsigned)std::max<int64_t>(1, std::min<int64_t>((cnt + 1023) / 1024, kSMs * 16));
     }
 
+    double tiny_rel = kTinyRel;  // asm_lp_params.tiny_rel of the current solve
     int precondition(int ruiz_iters, int warm) {
         LpView v = view();
         const Geo gr = geo_for(m, B), gc = geo_for(n, B), gm = geo_for(std::max(n, m), B);
@@ -1080,7 +1083,7 @@ class LpSolver {
         {
             const Geo gz = geo_for(std::max<int64_t>(nnz, 1), B);
             ASM_KB(k_absmax, gz, v, nnz);
-            ASM_KL(k_final_max<<<B, kFinalThreads, 0, stream>>>(partials.p, (int)gz.grid.x, B, gmax.p));
+            ASM_KL(k_final_max<<<B, kFinalThreads, 0, stream>>>(partials.p, (int)gz.grid.x, B, gmax.p, tiny_rel / kTinyRel));
         }
         for (int it = 0; it <= ruiz_iters; ++it) {
             if (it == ruiz_iters) {  // last pass: Pock-Chambolle (alpha = 1): 1-norms
@@ -1497,6 +1500,7 @@ class LpSolver {
         *flag = Buser;
         ASM_CK(cudaMemcpyAsync(prm.p, pdp, sizeof dp, cudaMemcpyHostToDevice, stream));
         ASM_CK(cudaMemcpyAsync(n_active.p, flag, sizeof(int), cudaMemcpyHostToDevice, stream));
+        tiny_rel = P.tiny_rel > 0.0 ? P.tiny_rel : kTinyRel;
         ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && has_solution) ? (int)P.warm_start : 0));
         const int steps = std::max(2, (int)P.check_every);
         // engine: 1 = one launch per half iteration (batch-streaming through HBM, CUDA graph per check period),

@@ -279,11 +279,15 @@ __device__ inline void group_decide(ScenState &st, const DevParams &P, const dou
     if (pres <= P.eps_rel * (1.0 + st.nq_un) && dres <= P.eps_rel * (1.0 + st.nc_un) &&
         gap <= P.eps_rel * (1.0 + fabs(pobj) + fabs(dobj)))
         status = ASM_LP_OPTIMAL;
+    double dbg_robj = 0.0, dbg_kty = 0.0, dbg_nr = 0.0;
     if (status < 0) {
         const double nr = q[Q_RAY_MAX] / st.sc;
         if (nr > 0.0) {
             const double robj = (q[Q_RAY_ROW] + q[Q_RAY_COL]) * unit / nr;
             const double kty = q[Q_KTY_MAX] / st.sc / nr;
+            dbg_robj = robj;
+            dbg_kty = kty;
+            dbg_nr = nr;
             if (robj > P.eps_infeas * fmax(1.0, kty)) status = ASM_LP_INFEASIBLE;
         }
     }
@@ -325,8 +329,9 @@ __device__ inline void group_decide(ScenState &st, const DevParams &P, const dou
         }
     }
     if (P.verbose && s == 0 && blockIdx.x == 0)
-        printf("[pdhg-g] it %lld k %d pres %.3e dres %.3e gap %.3e pobj %.10e r %.3e w %.3e restarts %d%s\n", total, k,
-               pres, dres, gap, pobj, r, st.omega, st.restarts, restart ? " R" : "");
+        printf("[pdhg-g] it %lld k %d pres %.3e dres %.3e gap %.3e pobj %.10e r %.3e w %.3e restarts %d%s | ray: obj %.3e "
+               "(row %.3e col %.3e) kty %.3e norm %.3e\n", total, k, pres, dres, gap, pobj, r, st.omega, st.restarts,
+               restart ? " R" : "", dbg_robj, q[Q_RAY_ROW] * unit, q[Q_RAY_COL] * unit, dbg_kty, dbg_nr);
     st.restart_flag = restart;
     if (jit + 1 == steps) {
         st.total += steps;

@@ -71,7 +71,8 @@ typedef struct asm_lp_params {
                            /* streaming kernels hand the stragglers to the group kernel (default 0.5)        */
     double weight_balance; /* > 0: at restarts move the primal weight by (relative primal residual / relative dual  */
                            /* residual)^weight_balance instead of the PDLP rule (0 = PDLP rule, the default)          */
-    double reserved[1];
+    double tiny_rel;       /* rows / columns whose largest coefficient is below tiny_rel * max|K| are treated as     */
+                           /* empty by the equilibration (0 = default 1e-8)                                            */
 } asm_lp_params;
 void asm_lp_default_params(asm_lp_params *p);
 
