@@ -279,6 +279,16 @@ def run_ours(a):
     def sum_over_ranks(x):
         return shard.sum_over_ranks(x, device="cuda" if world > 1 else None)
 
+    # timing rule: inputs larger than L2, or flush L2 between timed steps (outside the timed region)
+    Bpad0 = 1 if S <= 1 else (32 if S <= 32 else ((S + 63) // 64) * 64)
+    working_set = Bpad0 * (16 * nnz_csr + 64 * n + 48 * m)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if working_set < 2 * (126 << 20) else None
+
+    def flush_l2():
+        if flush_buf is not None:
+            flush_buf.zero_()
+            torch.cuda.synchronize()
+
     lp.update(hin["x"], hin["f"], hin["df"], hin["E"], hin["dE"], hdelta, False)   # inputs resident
     for _ in range(a.warmup):
         resident_step()
@@ -289,6 +299,7 @@ def run_ours(a):
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(a.steps):
+        flush_l2()
         dev_ms += resident_step()
     sync_all()
     wall_resident = time.perf_counter() - t0
@@ -364,8 +375,10 @@ def run_ours(a):
                        "n": n, "m": m, "nnz_coo": nnz, "nnz_csr": nnz_csr, "eps_rel": a.eps,
                        "engine": eng, "optimal": int(n_opt), "pdhg_iterations_max": int(its_max),
                        "pdhg_iterations_mean": its_sum / total_scen,
-                       "l2": "no flush: the batch working set (%.0f MB) exceeds the 126 MB L2" %
-                             (Bpad * (16 * nnz_csr + 64 * n + 48 * m) / 1e6),
+                       "l2": ("no flush: the batch working set (%.0f MB per iteration) exceeds the 126 MB L2"
+                              if flush_buf is None else
+                              "working set %.0f MB per iteration: L2 flushed between timed steps by writing 256 MB")
+                             % (working_set / 1e6),
                        "wall_s_resident": wall_resident},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
