@@ -209,6 +209,32 @@ def test_large_batch_with_compaction(gpu):
     lpb.close()
 
 
+def test_batch_in_feasibility_restoration(gpu):
+    """A batch of restoration-phase LPs (subproblem.jl:250-382: elastic rows, slack columns, shifted right-hand
+    sides) of the toy NLP at scattered points: objective and slack sums per scenario against the oracle."""
+    from activesetmethods_b200.examples import small_nlps
+    from activesetmethods_b200.sublp import SubLp
+    pr = small_nlps.ToyNlp()
+    rng = np.random.default_rng(11)
+    B = 40
+    x = rng.uniform(-1.5, 1.5, (B, pr.n))
+    f = np.array([pr.eval_f(xx) for xx in x])
+    df = np.array([pr.eval_grad_f(xx, np.zeros(pr.n)) for xx in x])
+    E = np.array([pr.eval_g(xx, np.zeros(pr.m)) for xx in x])
+    dE = np.array([pr.eval_jac_g(xx, "eval", None, None, np.zeros(len(pr.j_str))) for xx in x])
+    lpb = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, batch=B, eps_rel=1e-8)
+    p, lam, mu_u, mu_l, slack, status = lpb.sub_optimize(x, f, df, E, dE, 1000.0, True)
+    pat = so.JacobianPattern(pr.m, pr.n, pr.j_str)
+    for s in range(B):
+        ref = so.SubLp(pat, pr.g_L, pr.g_U, pr.x_L, pr.x_U)
+        out = ref.solve(pat.assemble(dE[s]), df[s], f[s], E[s], x[s], 1000.0, True)
+        assert status[s] == out[5] == 0, (s, status[s], out[5])
+        obj = lpb.last_info[s]["objective"]
+        assert abs(obj - ref.last_objective) <= OBJ_RTOL * max(1.0, abs(ref.last_objective)), (s, obj, ref.last_objective)
+        assert abs(slack[s].sum() - obj) <= 1e-6 * max(1.0, abs(obj))      # restoration objective = sum of slacks
+    lpb.close()
+
+
 def test_generic_lp_against_highs(gpu):
     """B200LP as a general external LP optimizer: random feasible bounded LPs against HiGHS."""
     import scipy.sparse as sp
