@@ -1183,10 +1183,57 @@ class LpSolver {
         sm.maxNSR |= 1;   // (maxNSR + 1) + (maxNSC + 1) ints: keep the 16-bit arrays 8-byte aligned
         sm.maxNSC |= 1;
         sm.mats = 1;
+        sm.push = 0;
+        sm.maxPushR = sm.maxPushC = 0;
         if (sm.bytes() > kSmemLimit) sm.mats = 0;
+        if (sm.mats && G <= kMaxClusterG) {   // exchange through (distributed) shared memory when it fits too
+            std::vector<int> ptr, dst, base, cnt;
+            build_push(R, C, G, ptr, dst, base, cnt);
+            for (int c = 0; c < G; ++c) sm.maxPushR = std::max(sm.maxPushR, cnt[c]);
+            build_push(C, R, G, ptr, dst, base, cnt);
+            for (int c = 0; c < G; ++c) sm.maxPushC = std::max(sm.maxPushC, cnt[c]);
+            sm.push = 1;
+            if (sm.bytes() > kSmemLimit) {
+                sm.push = 0;
+                sm.maxPushR = sm.maxPushC = 0;
+            }
+        }
         return sm.bytes();
     }
     static bool plan_fits(size_t bytes) { return bytes > 0 && bytes <= kSmemLimit; }
+
+    // Push lists for the distributed-shared-memory exchange: `prod` is the side that produces the vector (rows
+    // produce y, columns produce xbar), `cons` the side whose halo lists name the entries it gathers.  For every
+    // slot of every producing block: the (consumer rank << 16 | halo position) pairs, CSR by slot; ptr arrays are
+    // concatenated per block with one extra entry each.
+    static void build_push(const SellSide &prod, const SellSide &cons, int G, std::vector<int> &ptr, std::vector<int> &dst,
+                           std::vector<int> &dst_base, std::vector<int> &dst_cnt) {
+        ptr.clear();
+        dst.clear();
+        dst_base.assign(G, 0);
+        dst_cnt.assign(G, 0);
+        int total = 0;
+        for (int c = 0; c < G; ++c) total = std::max(total, prod.first[c] + prod.cnt[c]);
+        std::vector<std::vector<int>> who(total);
+        for (int c = 0; c < G; ++c)
+            for (int t = 0; t < cons.halo_cnt[c]; ++t) who[cons.halo[cons.halo_base[c] + t]].push_back((c << 16) | t);
+        for (int o = 0; o < G; ++o) {
+            dst_base[o] = (int)dst.size();
+            const int nslot = prod.nslice[o] * 32;
+            int local = 0;
+            for (int sl = 0; sl < nslot; ++sl) {
+                ptr.push_back(local);
+                const int id = prod.slot[prod.slot_base[o] + sl];
+                if (id >= 0)
+                    for (int w : who[id]) {
+                        dst.push_back(w);
+                        ++local;
+                    }
+            }
+            ptr.push_back(local);
+            dst_cnt[o] = local;
+        }
+    }
 
     const std::pair<size_t, int> &feasible(int G) {
         auto it = feas.find(G);
@@ -1229,7 +1276,8 @@ class LpSolver {
         return G;
     }
 
-    static const void *group_kernel(bool cluster, bool mats) {
+    static const void *group_kernel(bool cluster, bool mats, bool push = false) {
+        if (cluster && mats && push) return (const void *)k_pdhg_group<true, true, true>;
         if (cluster) return mats ? (const void *)k_pdhg_group<true, true> : (const void *)k_pdhg_group<true, false>;
         return mats ? (const void *)k_pdhg_group<false, true> : (const void *)k_pdhg_group<false, false>;
     }
@@ -1275,6 +1323,36 @@ class LpSolver {
         }
         pl->totSellR = (int)R.src.size();
         pl->totSellC = (int)C.src.size();
+        if (pl->sm.push && getenv("ASM_NO_PUSH")) {   // debugging switch: exchange through L2 instead
+            pl->sm.push = 0;
+            pl->sm.maxPushR = pl->sm.maxPushC = 0;
+        }
+        {
+            std::vector<int> ptr, dst, base, cnt;
+            auto upl = [&](DBuf<int> &b, const std::vector<int> &h) -> int {
+                ASM_TRY(b.alloc(std::max<size_t>(h.size(), 1)));
+                if (!h.empty()) ASM_CK(cudaMemcpy(b.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+                return ASM_OK;
+            };
+            if (pl->sm.push) {
+                build_push(R, C, G, ptr, dst, base, cnt);
+                for (int c = 0; c < G; ++c) {
+                    pl->cta[c].pushR_base = base[c];
+                    pl->cta[c].pushR_cnt = cnt[c];
+                }
+                ASM_TRY(upl(pl->pushR_ptr, ptr));
+                ASM_TRY(upl(pl->pushR_dst, dst));
+                build_push(C, R, G, ptr, dst, base, cnt);
+                for (int c = 0; c < G; ++c) {
+                    pl->cta[c].pushC_base = base[c];
+                    pl->cta[c].pushC_cnt = cnt[c];
+                }
+                ASM_TRY(upl(pl->pushC_ptr, ptr));
+                ASM_TRY(upl(pl->pushC_dst, dst));
+            } else {
+                for (int c = 0; c < G; ++c) pl->cta[c].pushR_base = pl->cta[c].pushR_cnt = pl->cta[c].pushC_base = pl->cta[c].pushC_cnt = 0;
+            }
+        }
         auto up = [&](DBuf<int> &b, const std::vector<int> &h) -> int {
             ASM_TRY(b.alloc(std::max<size_t>(h.size(), 1)));
             if (!h.empty()) ASM_CK(cudaMemcpy(b.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -1299,7 +1377,7 @@ class LpSolver {
         // how many groups can be resident at once
         const size_t smem = pl->sm.bytes();
         int groups = 1;
-        const void *fn = group_kernel(pl->cluster, pl->sm.mats != 0);
+        const void *fn = group_kernel(pl->cluster, pl->sm.mats != 0, pl->sm.push != 0);
         ASM_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (pl->cluster) {
             if (G > 8) ASM_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1367,6 +1445,10 @@ class LpSolver {
         a.haloC = pl.haloC.p;
         a.tailR = pl.tailR.p;
         a.tailC = pl.tailC.p;
+        a.pushR_ptr = pl.pushR_ptr.p;
+        a.pushR_dst = pl.pushR_dst.p;
+        a.pushC_ptr = pl.pushC_ptr.p;
+        a.pushC_dst = pl.pushC_dst.p;
         a.gA = pl.gA.p;
         a.gAT = pl.gAT.p;
         a.gconst = pl.gconst.p;
@@ -1397,7 +1479,7 @@ class LpSolver {
         ASM_TRY(pl.queue.zero(stream));
         const size_t smem = pl.sm.bytes();
         const unsigned grid = (unsigned)(pl.n_groups * pl.G);
-        const void *fn = group_kernel(pl.cluster, pl.sm.mats != 0);
+        const void *fn = group_kernel(pl.cluster, pl.sm.mats != 0, pl.sm.push != 0);
         void *args[] = {(void *)&a};
         // plans of different group sizes share the kernel: the attribute must match this launch
         ASM_CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1584,7 +1666,8 @@ class LpSolver {
             ASM_CK(cudaStreamSynchronize(stream));
             if (trace) {
                 fprintf(stderr, "[asm] group launch: %d LPs, G = %d (%s, matrix %s), %d groups resident, %.3f s\n", live,
-                        plan->G, plan->cluster ? "cluster" : "grid", plan->sm.mats ? "resident" : "streamed", plan->n_groups,
+                        plan->G, plan->cluster ? (plan->sm.push ? "cluster, DSMEM exchange" : "cluster") : "grid",
+                        plan->sm.mats ? "resident" : "streamed", plan->n_groups,
                         now() - t_phase);
                 t_phase = now();
             }

@@ -12,12 +12,17 @@
 // and gathers from there (an SM sustains only ~0.5 scattered global loads per cycle, but ~8 shared ones).
 // A block owns a contiguous range of rows and of columns; a warp owns 32-slot slices.  Blocks of a group meet at
 // two barriers per iteration:
-//   CLUSTER mode  G <= 16 : the group is a thread-block cluster, barrier = barrier.cluster (hardware)
+//   CLUSTER mode  G <= 16 : the group is a thread-block cluster, barrier = barrier.cluster (hardware); when the push
+//                           lists fit (PUSH) the exchange does not touch L2 at all: the block that computes an
+//                           entry of xbar (y) stores it straight into the halo buffers of the blocks that need it,
+//                           through distributed shared memory, and the cluster barrier publishes the stores
 //   GRID mode     G  > 16 : cooperative launch, barrier = one global counter per group
 // Groups pull LPs of the batch from an atomic queue, so every LP stops at its own convergence.
 // The KKT / restart / primal-weight logic is the one of lp_solver.cuh (k_decide), evaluated redundantly and
 // bit-identically by every block of the group from the same ordered partial sums.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "util.cuh"
 
 namespace asmb {
@@ -30,12 +35,14 @@ constexpr int kMaxSteps = 256;  // check_every is capped to this in the group en
 struct GroupCta {
     int r0, nR, nSR, sellR_base, sellR_cnt, ptrR_base, slotR_base, haloR_base, haloR_cnt;
     int c0, nC, nSC, sellC_base, sellC_cnt, ptrC_base, slotC_base, haloC_base, haloC_cnt;
+    int pushR_base, pushR_cnt, pushC_base, pushC_cnt;  // consumers of this block's y (rows) and xbar (columns)
 };
 
 // shared-memory carve (element counts are the maxima over the blocks of the group)
 struct GroupSmem {
     int maxSellR, maxSellC, maxRpad, maxCpad, maxNSR, maxNSC, maxHaloR, maxHaloC;
     int mats;  // 1: matrix values in shared memory, 0: streamed from L2
+    int push, maxPushR, maxPushC;  // 1: exchange through distributed shared memory (cluster, mats only)
     size_t bytes() const {
         size_t b = 0;
         if (mats) b += sizeof(double) * ((size_t)maxSellR + maxSellC);
@@ -47,6 +54,7 @@ struct GroupSmem {
         b += sizeof(int) * ((size_t)maxHaloR + maxHaloC + maxRpad + maxCpad + maxNSR + 1 + maxNSC + 1);
         b += sizeof(unsigned short) * ((size_t)maxSellR + maxSellC);
         b += (size_t)maxRpad + maxCpad;  // tail bytes
+        if (push) b += sizeof(int) * ((size_t)maxRpad + 1 + maxCpad + 1 + maxPushR + maxPushC + 4);
         return b + 64;
     }
 };
@@ -59,6 +67,7 @@ struct GroupPlan {
     DBuf<GroupCta> d_cta;
     DBuf<int> sellR_src, sellR_idx, ptrR, slotR, haloR, sellC_src, sellC_idx, ptrC, slotC, haloC;
     DBuf<unsigned char> tailR, tailC;
+    DBuf<int> pushR_ptr, pushR_dst, pushC_ptr, pushC_dst;  // per slot: (consumer rank << 16 | halo position) lists
     int totSellR = 0, totSellC = 0;
     DBuf<double> gA, gAT;  // per resident group: matrix values in sliced-ELL order (streamed when !mats)
     DBuf<double> gconst;   // per resident group and block: rl, ru, c, lb, ub by slot (when !mats)
@@ -190,6 +199,7 @@ struct GroupArgs {
     const GroupCta *cta;
     const int *sellR_src, *sellR_idx, *ptrR, *slotR, *haloR, *sellC_src, *sellC_idx, *ptrC, *slotC, *haloC;
     const unsigned char *tailR, *tailC;
+    const int *pushR_ptr, *pushR_dst, *pushC_ptr, *pushC_dst;
     double *gA, *gAT;  // [groups][totSellR], [groups][totSellC]
     double *gconst;    // [groups][G][2 maxRpad + 3 maxCpad]
     int totSellR, totSellC;
@@ -375,7 +385,29 @@ __device__ __forceinline__ double sell_dot(const double *__restrict__ sval, cons
     return split ? seg_reduce(acc, tail) : acc;
 }
 
-template <bool CLUSTER, bool MATS>
+// store `val` into the halo buffer of every block of the cluster that gathers this entry
+__device__ __forceinline__ void push_halo(double *halo_local, const int *__restrict__ ptr, const int *__restrict__ dst,
+                                          int sl, double val, int my_rank) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    if (my_rank < 0) {   // one-block group: every consumer is this block
+        for (int k = ptr[sl]; k < ptr[sl + 1]; ++k) halo_local[dst[k] & 0xffff] = val;
+        return;
+    }
+    for (int k = ptr[sl]; k < ptr[sl + 1]; ++k) {
+        const int t = dst[k];
+        cl.map_shared_rank(halo_local, t >> 16)[t & 0xffff] = val;
+    }
+}
+// barrier that publishes (distributed-)shared-memory stores; a one-block group only needs the block barrier
+__device__ __forceinline__ void cluster_sync_dsm(int G) {
+    if (G == 1)
+        __syncthreads();
+    else
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool CLUSTER, bool MATS, bool PUSH = false>
 __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const LpView &v = a.v;
@@ -411,6 +443,11 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
     unsigned short *t_idx = a_idx + a.sm.maxSellR;
     unsigned char *tailR = reinterpret_cast<unsigned char *>(t_idx + a.sm.maxSellC);
     unsigned char *tailC = tailR + a.sm.maxRpad;
+    // push lists (PUSH only), 4-byte aligned after the tail bytes
+    int *spushR_ptr = reinterpret_cast<int *>(reinterpret_cast<size_t>(tailC + a.sm.maxCpad + 3) & ~(size_t)3);
+    int *spushC_ptr = spushR_ptr + a.sm.maxRpad + 1;
+    int *spushR_dst = spushC_ptr + a.sm.maxCpad + 1;
+    int *spushC_dst = spushR_dst + a.sm.maxPushR;
     __shared__ ScenState st;
     __shared__ double wtab[kMaxSteps];
     __shared__ DevParams P;
@@ -429,6 +466,12 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
     for (int i = tid; i < d.nSC * 32; i += kGThreads) {
         cmap[i] = a.slotC[d.slotC_base + i];
         tailC[i] = a.tailC[d.slotC_base + i];
+    }
+    if (PUSH) {
+        for (int i = tid; i <= d.nSR * 32; i += kGThreads) spushR_ptr[i] = a.pushR_ptr[d.slotR_base + rank + i];
+        for (int i = tid; i <= d.nSC * 32; i += kGThreads) spushC_ptr[i] = a.pushC_ptr[d.slotC_base + rank + i];
+        for (int i = tid; i < d.pushR_cnt; i += kGThreads) spushR_dst[i] = a.pushR_dst[d.pushR_base + i];
+        for (int i = tid; i < d.pushC_cnt; i += kGThreads) spushC_dst[i] = a.pushC_dst[d.pushC_base + i];
     }
     for (int i = tid; i <= d.nSR; i += kGThreads) ptrR[i] = a.ptrR[d.ptrR_base + i];
     for (int i = tid; i <= d.nSC; i += kGThreads) ptrC[i] = a.ptrC[d.ptrC_base + i];
@@ -506,6 +549,10 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
             sub[sl] = u;
         }
         group_sync<CLUSTER>(bar, epoch, G);
+        if (PUSH) {   // the halos are kept current by the pushes from here on
+            halo_fetch(hy, gy, listC, d.haloC_cnt);
+            cluster_sync_dsm(G);
+        }
 
         const bool live0 = true;
         long long it = st.total;
@@ -524,7 +571,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                 const double w = wtab[j];
                 if (!check) {
                     // ------------------------------ primal half
-                    halo_fetch(hy, gy, listC, d.haloC_cnt);
+                    if (!PUSH) halo_fetch(hy, gy, listC, d.haloC_cnt);
                     for (int q = warp; q < d.nSC; q += kGWarps) {
                         const int sl = q * 32 + lane;
                         const int p0 = ptrC[q] * 32 + lane, len = ptrC[q + 1] - ptrC[q];
@@ -534,12 +581,20 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                         const double xv = sx[sl];
                         const double xpv = fmin(fmax(xv - tau * (scc[sl] - acc), slb[sl]), sub[sl]);
                         const double xb = 2.0 * xpv - xv;
-                        if (gj >= 0) gx[gj] = xb;
+                        if (gj >= 0) {
+                            if (PUSH)
+                                push_halo(hx, spushC_ptr, spushC_dst, sl, xb, G == 1 ? -1 : rank);
+                            else
+                                gx[gj] = xb;
+                        }
                         sx[sl] = w * xb + (1.0 - w) * sxa[sl];
                     }
-                    group_sync<CLUSTER>(bar, epoch, G);
+                    if (PUSH)
+                        cluster_sync_dsm(G);
+                    else
+                        group_sync<CLUSTER>(bar, epoch, G);
                     // ------------------------------ dual half
-                    halo_fetch(hx, gx, listR, d.haloR_cnt);
+                    if (!PUSH) halo_fetch(hx, gx, listR, d.haloR_cnt);
                     for (int q = warp; q < d.nSR; q += kGWarps) {
                         const int sl = q * 32 + lane;
                         const int p0 = ptrR[q] * 32 + lane, len = ptrR[q + 1] - ptrR[q];
@@ -552,9 +607,17 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                         const double ypv = t < l ? sigma * (l - t) : (t > u ? sigma * (u - t) : 0.0);
                         const double yn = w * (2.0 * ypv - yv) + (1.0 - w) * sya[sl];
                         sy[sl] = yn;
-                        if (gi >= 0) gy[gi] = yn;
+                        if (gi >= 0) {
+                            if (PUSH)
+                                push_halo(hy, spushR_ptr, spushR_dst, sl, yn, G == 1 ? -1 : rank);
+                            else
+                                gy[gi] = yn;
+                        }
                     }
-                    group_sync<CLUSTER>(bar, epoch, G);
+                    if (PUSH)
+                        cluster_sync_dsm(G);
+                    else
+                        group_sync<CLUSTER>(bar, epoch, G);
                     continue;
                 }
                 // ================================== check iteration ==========================================
@@ -562,7 +625,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                 double acc[Q_COUNT];
 #pragma unroll
                 for (int i = 0; i < Q_COUNT; ++i) acc[i] = 0.0;
-                halo_fetch(hy, gy, listC, d.haloC_cnt);
+                if (!PUSH) halo_fetch(hy, gy, listC, d.haloC_cnt);
                 for (int q = warp; q < d.nSC; q += kGWarps) {
                     const int sl = q * 32 + lane;
                     const int p0 = ptrC[q] * 32 + lane, len = ptrC[q + 1] - ptrC[q];
@@ -573,6 +636,7 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                     const double cj = scc[sl], xv = sx[sl];
                     const double xpv = fmin(fmax(xv - tau * (cj - s1), slb[sl]), sub[sl]);
                     gx[gj] = 2.0 * xpv - xv;
+                    if (PUSH) push_halo(hx, spushC_ptr, spushC_dst, sl, 2.0 * xpv - xv, G == 1 ? -1 : rank);
                     gx2[gj] = xv;
                     gxp[gj] = xpv;
                     const double dx = xpv - xv, da = xpv - sxa[sl];
@@ -581,8 +645,9 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                     acc[Q_POBJ] += cj * xpv;
                 }
                 group_sync<CLUSTER>(bar, epoch, G);
+                if (PUSH) cluster_sync_dsm(G);
                 const double inv_sb = 1.0 / st.sb, inv_sc = 1.0 / st.sc;
-                halo_fetch(hx, gx, listR, d.haloR_cnt);
+                if (!PUSH) halo_fetch(hx, gx, listR, d.haloR_cnt);
                 for (int q = warp; q < d.nSR; q += kGWarps) {
                     const int sl = q * 32 + lane;
                     const int p0 = ptrR[q] * 32 + lane, len = ptrR[q + 1] - ptrR[q];
@@ -687,9 +752,11 @@ __global__ void __launch_bounds__(kGThreads, 1) k_pdhg_group(const GroupArgs a) 
                     }
                     sy[sl] = yn;
                     gy[gi] = yn;
+                    if (PUSH) push_halo(hy, spushR_ptr, spushR_dst, sl, yn, G == 1 ? -1 : rank);
                 }
                 if (st.status >= 0) done = true;
                 group_sync<CLUSTER>(bar, epoch, G);
+                if (PUSH) cluster_sync_dsm(G);
             }
             it += a.steps;
         }
