@@ -435,3 +435,194 @@ class SlpTR(_Slp):
             self.iter += 1
         self.finish()
         return self
+
+
+class SlpLSBatch:
+    """B independent line-search SLP solves that share one Jacobian pattern (load scenarios of one network,
+    BASELINE config 5), advanced in lock-step so that every round is **one** batched call of the device hot path:
+    one `update`, the KKT reductions, one sub-LP batch solve (two when some scenarios are in feasibility
+    restoration), and one batched merit evaluation per backtracking round.  Per scenario the control flow is
+    exactly ``SlpLS.run`` (reference ``slp_line_search.jl:78-215``) — a scenario that terminates simply stops
+    moving while the others go on.  ``problems`` are objects with the ``Model.from_problem`` interface."""
+
+    def __init__(self, problems, parameters: Parameters | None = None):
+        self.problems = list(problems)
+        self.options = parameters if parameters is not None else Parameters()
+        p0 = self.problems[0]
+        self.B, self.n, self.m = len(self.problems), p0.n, p0.m
+        for pr in self.problems:
+            assert pr.n == self.n and pr.m == self.m and np.array_equal(pr.j_str, p0.j_str), \
+                "batched scenarios must share the Jacobian pattern"
+        B, n, m = self.B, self.n, self.m
+        self.x = np.array([np.array(pr.x0, dtype=float) for pr in self.problems])
+        self.f = np.zeros(B)
+        self.df = np.zeros((B, n))
+        self.E = np.zeros((B, m))
+        self.dE = np.zeros((B, len(p0.j_str)))
+        self.p = np.zeros((B, n))
+        self.lam = np.zeros((B, m))
+        self.mult_x_U = np.zeros((B, n))
+        self.mult_x_L = np.zeros((B, n))
+        self.nu = np.zeros((B, m))
+        self.iter = np.ones(B, dtype=np.int64)
+        self.ret = np.full(B, -5, dtype=np.int64)
+        self.running = np.ones(B, dtype=bool)
+        self.fr = np.zeros(B, dtype=bool)
+        self.alpha = np.zeros(B)
+        self.prim_infeas = np.full(B, INF)
+        self.dual_infeas = np.full(B, INF)
+        self.compl = np.full(B, INF)
+        self.obj_val = np.zeros(B)
+        self.rounds = 0
+        self.lp_iterations = 0
+        self.optimizer = None
+
+    def _instantiate(self):
+        o = self.options
+        prs = self.problems
+        arr = lambda name: np.array([np.asarray(getattr(pr, name), dtype=float) for pr in prs])  # noqa: E731
+        if o.external_optimizer == "B200LP":
+            opt = SubLp(self.n, self.m, prs[0].j_str, arr("x_L"), arr("x_U"), arr("g_L"), arr("g_U"), batch=self.B,
+                        device=o.device, **{"warm_start": 1, **o.lp_options})
+            opt._squeeze = False
+            return opt
+        return o.external_optimizer(self.n, self.m, prs[0].j_str, arr("x_L"), arr("x_U"), arr("g_L"), arr("g_U"),
+                                    batch=self.B)
+
+    def _eval(self, s):
+        pr = self.problems[s]
+        self.f[s] = pr.eval_f(self.x[s])
+        pr.eval_grad_f(self.x[s], self.df[s])
+        pr.eval_g(self.x[s], self.E[s])
+        pr.eval_jac_g(self.x[s], "eval", None, None, self.dE[s])
+
+    def _solve_phase(self, fr):
+        """Sub-LP batch of one phase; returns the extract tuple plus phi(0) and the directional derivative computed
+        while the device still holds this phase's step and slacks."""
+        opt = self.optimizer
+        if fr:                      # the normal-phase data push was done for the KKT metrics of this round
+            opt.update(self.x, self.f, self.df, self.E, self.dE, 1000.0, True)
+        p, lam, mu_u, mu_l, slack, status = opt.solve_extract()
+        info = getattr(opt, "last_info", None) or []
+        self.lp_iterations += int(sum(i.get("iterations") or 0 for i in info))
+        return [np.atleast_2d(a) if np.ndim(a) < 2 else a for a in (p, lam, mu_u, mu_l)] + [slack, np.atleast_1d(status)]
+
+    def run(self):
+        o = self.options
+        B = self.B
+        for s, pr in enumerate(self.problems):                              # slp_line_search.jl:96-105
+            lo = pr.x_L > -INF
+            self.x[s][lo] = np.maximum(self.x[s][lo], pr.x_L[lo])
+            up = pr.x_U > -INF
+            self.x[s][up] = np.minimum(self.x[s][up], pr.x_U[up])
+        if self.optimizer is None:
+            self.optimizer = self._instantiate()
+        opt = self.optimizer
+        while self.running.any():
+            self.rounds += 1
+            run = np.nonzero(self.running)[0]
+            for s in run:
+                self._eval(s)
+            # KKT metrics with last round's multipliers on this round's Jacobian (App. C-7)
+            opt.update(self.x, self.f, self.df, self.E, self.dE, 1000.0, False)
+            self.prim_infeas[run] = np.atleast_1d(opt.norm_violations(None, None, INF))[run]
+            self.dual_infeas[run] = np.atleast_1d(opt.kt_residuals(self.lam, self.mult_x_U, self.mult_x_L))[run]
+            self.compl[run] = np.atleast_1d(opt.norm_complementarity(self.lam))[run]
+            need = {False: self.running & ~self.fr, True: self.running & self.fr}
+            status = np.zeros(B, dtype=np.int64)
+            phi0 = np.zeros(B)
+            deriv = np.zeros(B)
+            for fr in (False, True):
+                sel = need[fr]
+                if not sel.any():
+                    continue
+                p, lam, mu_u, mu_l, slack, st = self._solve_phase(fr)
+                idx = np.nonzero(sel)[0]
+                self.p[idx], self.lam[idx], self.mult_x_U[idx], self.mult_x_L[idx] = p[idx], lam[idx], mu_u[idx], mu_l[idx]
+                status[idx] = st[idx]
+                ok = idx[st[idx] == LP_OPTIMAL]
+                # compute_nu! (:251-261) then phi(0) and D with this phase's device state
+                first = ok[self.iter[ok] == 1]
+                later = ok[self.iter[ok] != 1]
+                self.nu[first] = np.abs(self.lam[first])
+                self.nu[later] = np.maximum(self.nu[later], np.abs(self.lam[later]))
+                base = self.prim_infeas if fr else self.f
+                phi0[sel] = np.atleast_1d(opt.merit_phi(base, None, self.nu, np.zeros(B), fr))[sel]
+                deriv[sel] = np.atleast_1d(opt.merit_derivative(self.nu, fr))[sel]
+                self._line_search(fr, ok, phi0, deriv)
+            # ---- per-scenario control flow of run! (:127-205)
+            for s in run:
+                st = status[s]
+                if st not in (LP_OPTIMAL, LP_INFEASIBLE):
+                    if self.prim_infeas[s] <= o.tol_infeas:
+                        self.ret[s] = 6
+                    self.running[s] = False
+                    continue
+                if st == LP_INFEASIBLE:
+                    if self.fr[s]:
+                        self.ret[s] = 6 if self.prim_infeas[s] <= o.tol_infeas else 2
+                        self.running[s] = False
+                    else:
+                        self.fr[s] = True                                   # re-solved next round, iter unchanged
+                    continue
+                if self.iter[s] >= o.max_iter:
+                    self.ret[s] = 6 if self.prim_infeas[s] <= o.tol_infeas else -1
+                    self.running[s] = False
+                    continue
+                if (self.prim_infeas[s] <= o.tol_infeas and self.compl[s] <= o.tol_residual) or \
+                        float(np.max(np.abs(self.p[s]))) <= o.tol_direction:
+                    if self.fr[s]:
+                        self.fr[s] = False
+                        self.iter[s] += 1
+                        continue
+                    elif self.dual_infeas[s] <= o.tol_residual:
+                        self.ret[s] = 0
+                        self.running[s] = False
+                        continue
+                if not self._valid[s]:
+                    if self._ret3[s]:
+                        self.ret[s] = 6 if self.prim_infeas[s] <= o.tol_infeas else 2
+                        self.running[s] = False
+                    else:
+                        self.fr[s] = True
+                        self.iter[s] += 1
+                    continue
+                self.x[s] = self.x[s] + self.alpha[s] * self.p[s]
+                self.iter[s] += 1
+        for s, pr in enumerate(self.problems):
+            self.obj_val[s] = pr.eval_f(self.x[s])
+        return self
+
+    def _line_search(self, fr, idx, phi0, deriv):
+        """compute_alpha (:222-244) for the scenarios ``idx`` of one phase, one batched merit call per trial round."""
+        o = self.options
+        B = self.B
+        if not hasattr(self, "_valid"):
+            self._valid = np.ones(B, dtype=bool)
+            self._ret3 = np.zeros(B, dtype=bool)
+        self._valid[idx] = True
+        self._ret3[idx] = False
+        self.alpha[idx] = 1.0
+        searching = np.zeros(B, dtype=bool)
+        searching[idx] = True
+        base = np.zeros(B)
+        Et = self.E.copy()
+        while searching.any():
+            act = np.nonzero(searching)[0]
+            for s in act:
+                pr = self.problems[s]
+                xt = self.x[s] + self.alpha[s] * self.p[s]
+                pr.eval_g(xt, Et[s])
+                base[s] = self.prim_infeas[s] if fr else pr.eval_f(xt)
+            phi = np.atleast_1d(self.optimizer.merit_phi(base, Et, self.nu, self.alpha, fr))
+            for s in act:
+                if phi[s] > phi0[s] + o.eta * self.alpha[s] * deriv[s]:
+                    if self.alpha[s] < o.min_alpha:
+                        if fr:
+                            self._ret3[s] = True
+                        self._valid[s] = False
+                        searching[s] = False
+                    else:
+                        self.alpha[s] *= o.tau
+                else:
+                    searching[s] = False

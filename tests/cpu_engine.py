@@ -79,3 +79,39 @@ class OracleEngine:
 
     def close(self):
         pass
+
+
+class OracleBatchEngine:
+    """Batch twin of ``OracleEngine`` (one oracle engine per scenario) with the ``SubLp(batch=B)`` conventions:
+    arrays are ``[B, ...]``, the restoration flag is shared by the call."""
+
+    def __init__(self, n, m, j_str, x_L, x_U, g_L, g_U, batch=1, **_):
+        self.B = batch
+        self.eng = [OracleEngine(n, m, j_str, x_L[s], x_U[s], g_L[s], g_U[s]) for s in range(batch)]
+        self.last_info = None
+
+    def update(self, x_k, f, df, E, dE, delta, feasibility=False):
+        for s, e in enumerate(self.eng):
+            e.update(x_k[s], f[s], df[s], E[s], dE[s], delta, feasibility)
+
+    def solve_extract(self):
+        outs = [e.solve_extract() for e in self.eng]
+        self.last_info = [e.last_info[0] for e in self.eng]
+        return tuple(np.array([o[k] for o in outs]) for k in range(6))
+
+    def norm_violations(self, E=None, x=None, p=1):
+        return np.array([e.norm_violations(None if E is None else E[s], None if x is None else x[s], p)
+                         for s, e in enumerate(self.eng)])
+
+    def kt_residuals(self, lam, mu_u, mu_l):
+        return np.array([e.kt_residuals(lam[s], mu_u[s], mu_l[s]) for s, e in enumerate(self.eng)])
+
+    def norm_complementarity(self, lam):
+        return np.array([e.norm_complementarity(lam[s]) for s, e in enumerate(self.eng)])
+
+    def merit_phi(self, base, E_trial, nu, alpha, feasibility=False):
+        return np.array([e.merit_phi(base[s], None if E_trial is None else E_trial[s], nu[s], alpha[s], feasibility)
+                         for s, e in enumerate(self.eng)])
+
+    def merit_derivative(self, nu, feasibility=False):
+        return np.array([e.merit_derivative(nu[s], feasibility) for s, e in enumerate(self.eng)])

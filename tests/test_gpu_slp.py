@@ -88,6 +88,25 @@ def test_case9_line_search_status_and_tolerance(gpu):
     assert _violation(pr, slp.x) <= 1e-2
 
 
+def test_batched_scenarios_line_search(gpu):
+    """Six load scenarios of case9 solved together by the lock-step batched driver (one batched device call per SLP
+    round) : every scenario ends LOCALLY_SOLVED, feasible, and within the reference's suite tolerance of the optimum
+    the oracle's trust-region run finds for that scenario."""
+    from activesetmethods_b200.slp import Parameters, SlpLSBatch
+    net = acopf.case9()
+    ids = [1, 2, 3, 4, 5, 6]
+    probs = [acopf.AcopfModel(acopf.perturb_loads(net, s)) for s in ids]
+    batch = SlpLSBatch(probs, Parameters(max_iter=100, lp_options=LP)).run()
+    assert batch.rounds <= 120 and batch.lp_iterations > 0
+    for k, s in enumerate(ids):
+        ref = so.optimize(acopf.AcopfModel(acopf.perturb_loads(net, s)),
+                          so.Parameters(algorithm="Trust Region", max_iter=200, tol_residual=1e-4, tol_infeas=1e-4))
+        assert batch.ret[k] in (0, 6), (s, batch.ret[k])
+        assert _violation(probs[k], batch.x[k]) <= 1e-2
+        assert ref.ret in (0, 6)
+        assert abs(batch.obj_val[k] - ref.obj_val) <= 1e-2 * abs(ref.obj_val), (s, batch.obj_val[k], ref.obj_val)
+
+
 def test_missing_external_optimizer(gpu):
     """model.jl:64-66: no external optimizer -> Invalid_Option (-12)."""
     from activesetmethods_b200.slp import Model, Parameters, optimize

@@ -6,8 +6,8 @@ import numpy as np
 import pytest
 
 from activesetmethods_b200.examples import acopf, small_nlps
-from activesetmethods_b200.slp import Model, Parameters, SlpLS, SlpTR, optimize, STATUS
-from cpu_engine import OracleEngine
+from activesetmethods_b200.slp import Model, Parameters, SlpLS, SlpLSBatch, SlpTR, optimize, STATUS
+from cpu_engine import OracleBatchEngine, OracleEngine
 from oracle import slp_oracle as so
 from test_oracle_pins import case3_network
 
@@ -61,3 +61,28 @@ def test_trust_region_collapse_terminates():
     ref.clip_start = lambda: None
     ref.run()
     assert ref.ret == 6 and ref.iter == 25
+
+
+def test_batched_line_search_equals_single_runs():
+    """SlpLSBatch (lock-step over scenarios, one batched hot-path call per round) must give every scenario exactly what
+    its own SlpLS run gives: same status, iteration count and iterate, for load scenarios of case9 and for a batch
+    that mixes scenarios entering feasibility restoration (toy, started at different points)."""
+    net = acopf.case9()
+    probs = [acopf.AcopfModel(acopf.perturb_loads(net, s + 1)) for s in range(4)]
+    batch = SlpLSBatch(probs, Parameters(max_iter=100, external_optimizer=OracleBatchEngine)).run()
+    for s in range(4):
+        one = SlpLS(Model.from_problem(acopf.AcopfModel(acopf.perturb_loads(net, s + 1)),
+                                       Parameters(max_iter=100, external_optimizer=OracleEngine))).run()
+        assert batch.ret[s] == one.ret and batch.iter[s] == one.iter, (s, batch.ret[s], one.ret)
+        assert np.allclose(batch.x[s], one.x, rtol=0, atol=1e-9)
+        assert abs(batch.obj_val[s] - one.obj_val) <= 1e-9 * abs(one.obj_val)
+    toys = [small_nlps.ToyNlp() for _ in range(3)]
+    toys[1].x0 = np.array([0.5, -0.5])
+    toys[2].x0 = np.array([-2.0, -0.4])
+    tb = SlpLSBatch(toys, Parameters(max_iter=200, external_optimizer=OracleBatchEngine)).run()
+    for s in range(3):
+        pr = small_nlps.ToyNlp()
+        pr.x0 = toys[s].x0.copy()
+        one = SlpLS(Model.from_problem(pr, Parameters(max_iter=200, external_optimizer=OracleEngine))).run()
+        assert tb.ret[s] == one.ret and tb.iter[s] == one.iter, (s, tb.ret[s], one.ret, tb.iter[s], one.iter)
+        assert np.allclose(tb.x[s], one.x, rtol=0, atol=1e-9)
