@@ -14,11 +14,17 @@ import scipy.sparse as sp
 INF = math.inf
 
 
-def ruiz_pc_scale(K: sp.csr_matrix, ruiz_iters=10, pc=True):
+def ruiz_pc_scale(K: sp.csr_matrix, ruiz_iters=10, pc=True, tiny_rel=1e-8):
     m, n = K.shape
     dr = np.ones(m)
     dc = np.ones(n)
-    A = K.copy().tocsr()
+    # rows / columns whose largest coefficient is below tiny_rel * max|K| are numerically empty: they keep scale 1
+    # (kTinyRel in csrc/lp_solver.cuh); they are masked out while the factors are computed and restored at the end
+    a0 = abs(K).tocsr()
+    gmax = a0.max() if K.nnz else 0.0
+    keep_r = np.asarray(a0.max(axis=1).todense()).ravel() > tiny_rel * gmax
+    keep_c = np.asarray(a0.max(axis=0).todense()).ravel() > tiny_rel * gmax
+    A = (sp.diags(keep_r.astype(float)) @ K @ sp.diags(keep_c.astype(float))).tocsr()
     for _ in range(ruiz_iters):
         absA = abs(A)
         rmax = np.asarray(absA.max(axis=1).todense()).ravel()
@@ -37,6 +43,7 @@ def ruiz_pc_scale(K: sp.csr_matrix, ruiz_iters=10, pc=True):
         A = sp.diags(sr) @ A @ sp.diags(sc)
         dr *= sr
         dc *= sc
+    A = sp.diags(dr) @ K @ sp.diags(dc)
     return A.tocsr(), dr, dc
 
 
