@@ -1561,6 +1561,15 @@ class LpSolver {
     }
 
     int solve(const asm_lp_params &P, asm_lp_info *info) {
+        if (cur) {   // a previous solve failed half way through a compacted batch: back to the home batch
+            cur = nullptr;
+            B = homeB;
+            Buser = homeBuser;
+            if (graph_exec) {
+                cudaGraphExecDestroy(graph_exec);
+                graph_exec = nullptr;
+            }
+        }
         DevParams dp;
         dp.eps_rel = P.eps_rel;
         dp.eps_infeas = P.eps_infeas;
@@ -1585,15 +1594,11 @@ class LpSolver {
         tiny_rel = P.tiny_rel > 0.0 ? P.tiny_rel : kTinyRel;
         ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && has_solution) ? (int)P.warm_start : 0));
         const int steps = std::max(2, (int)P.check_every);
-        // engine: 1 = one launch per half iteration (batch-streaming through HBM, CUDA graph per check period),
-        //         2 = persistent on-chip group kernel, 0 = group kernel when the LP fits, else streaming
-        // engine 0: a single LP runs on the group kernel; a batch streams until a quarter of it is left, then the
-        // stragglers finish on the group kernel, each to its own convergence
-        if (cur) {   // a previous solve failed half way: back to the home batch
-            cur = nullptr;
-            B = homeB;
-            Buser = homeBuser;
-        }
+        // engine 1: streaming kernels only (one launch per half iteration, CUDA graph per check period);
+        // engine 2: persistent group kernel only;
+        // engine 0: a single LP runs on the group kernel; a batch streams, compacting the running LPs into a narrower
+        //           working set as they converge, and hands the stragglers to the group kernel when the cost model
+        //           says so -- every LP stops at its own convergence
         homeB = B;
         homeBuser = Buser;
         compactions = 0;
