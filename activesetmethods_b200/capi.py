@@ -41,6 +41,15 @@ class LpInfo(C.Structure):
     ]
 
 
+class AcopfDesc(C.Structure):
+    _fields_ = [
+        ("nb", C.c_int32), ("ng", C.c_int32), ("nl", C.c_int32), ("nd", C.c_int32), ("ref_bus", C.c_int32),
+        ("f_bus", c_int32_p), ("t_bus", c_int32_p), ("coef", c_double_p), ("gs", c_double_p), ("bs", c_double_p),
+        ("cost2", c_double_p), ("cost1", c_double_p), ("cost0", c_double_p), ("dc_loss1", c_double_p),
+        ("bal_ptr", c_int32_p), ("bal_col", c_int32_p), ("bal_coef", c_double_p),
+    ]
+
+
 class AsmError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"asm_b200 error {code}: {msg}")
@@ -87,6 +96,10 @@ SIGNATURES = {
     "asm_slp_row_norms": (C.c_int, [_VP, c_double_p]),
     "asm_slp_merit_phi": (C.c_int, [_VP, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int32, c_double_p]),
     "asm_slp_merit_derivative": (C.c_int, [_VP, c_double_p, C.c_int32, c_double_p]),
+    "asm_slp_attach_acopf": (C.c_int, [_VP, C.POINTER(AcopfDesc)]),
+    "asm_slp_eval_acopf": (C.c_int, [_VP, c_double_p, c_double_p, C.c_int32]),
+    "asm_slp_get_eval": (C.c_int, [_VP, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "asm_slp_acopf_trial": (C.c_int, [_VP, c_double_p, c_double_p, c_double_p, C.c_int32, c_double_p]),
     "asm_slp_launch_count": (C.c_int64, [_VP]),
     "asm_slp_last_solve_timing": (C.c_int, [_VP, c_double_p, c_int64_p]),
     "asm_plan_check": (C.c_int, [C.c_int32, C.c_int32, c_int64_p, c_int32_p, C.c_int32, c_int64_p, c_int32_p,

@@ -312,6 +312,139 @@ __global__ void __launch_bounds__(kFinalThreads) k_final(const double *partials,
     }
 }
 
+// =================================== device-side ACOPF evaluator ================================================
+// f, grad f, g and the Jacobian values of the ACP-polar OPF written straight into the SLP handle's
+// device buffers (the role of the JuMP NLPEvaluator callbacks at /root/reference/src/MOI_wrapper.jl:1047-1069 and
+// eval_functions!, src/algorithms/slp.jl:186-191), and compute_phi's trial evaluations g(x + alpha p), f(x + alpha p)
+// (slp.jl:79-115, slp_line_search.jl:228-241) without a host round trip.  Variable / row / Jacobian layout is the one
+// of activesetmethods_b200/examples/acopf.py (PowerModels' row classes in the order of MOI_wrapper.jl:683-689).
+struct AcopfDev {
+    int nb = 0, ng = 0, nl = 0, nd = 0, ref_bus = 0, nnz_bal = 0;
+    // variable offsets, row offsets, Jacobian block offsets
+    int o_va, o_vm, o_pg, o_qg, o_p, o_q, o_pdc, o_qdc;
+    int r_angmax, r_angmin, r_ref, r_dc, r_thermal, r_bal, r_ohm;
+    int k_angmax, k_angmin, k_ref, k_dc, k_thermal, k_bal, k_ohm;
+    const int *f_bus, *t_bus, *bal_ptr, *bal_col;
+    const double *coef, *gs, *bs, *cost2, *cost1, *cost0, *dc_loss1, *bal_coef;
+};
+struct AcopfIo {
+    const double *xk, *p, *alpha;   // evaluation point x = xk (+ alpha p when TRIAL)
+    double *f, *df, *E, *dE;        // outputs (df, dE unused when TRIAL)
+    int B;
+};
+template <bool TRIAL>
+__device__ __forceinline__ double acopf_x(const AcopfIo &io, int j, int s) {
+    const double v = io.xk[(int64_t)j * io.B + s];
+    return TRIAL ? v + io.alpha[s] * io.p[(int64_t)j * io.B + s] : v;
+}
+// one branch per item: angle-difference rows, thermal limits, Ohm's law rows and their derivatives
+template <bool BATCH, bool TRIAL>
+__global__ void __launch_bounds__(kThreads) k_acopf_branch(AcopfDev a, AcopfIo io) {
+    Map<BATCH> mp;
+    const int B = io.B, s = mp.s, nl = a.nl;
+    for (int64_t l = mp.first; l < nl; l += mp.stride) {
+        const int fb = a.f_bus[l], tb = a.t_bus[l];
+        const double vaf = acopf_x<TRIAL>(io, a.o_va + fb, s), vat = acopf_x<TRIAL>(io, a.o_va + tb, s);
+        const double vf = acopf_x<TRIAL>(io, a.o_vm + fb, s), vt = acopf_x<TRIAL>(io, a.o_vm + tb, s);
+        const double pf = acopf_x<TRIAL>(io, a.o_p + (int)l, s), qf = acopf_x<TRIAL>(io, a.o_q + (int)l, s);
+        const double pt = acopf_x<TRIAL>(io, a.o_p + nl + (int)l, s), qt = acopf_x<TRIAL>(io, a.o_q + nl + (int)l, s);
+        const double d = vaf - vat;
+        double sn, cs;
+        sincos(d, &sn, &cs);
+        const double vv = vf * vt;
+        double c[12];
+#pragma unroll
+        for (int t = 0; t < 12; ++t) c[t] = a.coef[(int64_t)t * nl + l];
+        auto E = [&](int row) -> double & { return io.E[(int64_t)row * B + s]; };
+        E(a.r_angmax + (int)l) = d;
+        E(a.r_angmin + (int)l) = d;
+        E(a.r_thermal + 2 * (int)l) = pf * pf + qf * qf;
+        E(a.r_thermal + 2 * (int)l + 1) = pt * pt + qt * qt;
+        const double e_pf = c[0] * vf * vf + c[1] * vv * cs + c[2] * vv * sn;
+        const double e_qf = c[3] * vf * vf + c[4] * vv * cs + c[5] * vv * sn;
+        const double e_pt = c[6] * vt * vt + c[7] * vv * cs - c[8] * vv * sn;
+        const double e_qt = c[9] * vt * vt + c[10] * vv * cs - c[11] * vv * sn;
+        E(a.r_ohm + 4 * (int)l) = pf - e_pf;
+        E(a.r_ohm + 4 * (int)l + 1) = qf - e_qf;
+        E(a.r_ohm + 4 * (int)l + 2) = pt - e_pt;
+        E(a.r_ohm + 4 * (int)l + 3) = qt - e_qt;
+        if (!TRIAL) {
+            auto J = [&](int k) -> double & { return io.dE[(int64_t)k * B + s]; };
+            J(a.k_angmax + 2 * (int)l) = 1.0;
+            J(a.k_angmax + 2 * (int)l + 1) = -1.0;
+            J(a.k_angmin + 2 * (int)l) = 1.0;
+            J(a.k_angmin + 2 * (int)l + 1) = -1.0;
+            J(a.k_thermal + 4 * (int)l) = 2.0 * pf;
+            J(a.k_thermal + 4 * (int)l + 1) = 2.0 * qf;
+            J(a.k_thermal + 4 * (int)l + 2) = 2.0 * pt;
+            J(a.k_thermal + 4 * (int)l + 3) = 2.0 * qt;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double aa = c[3 * r], bb = c[3 * r + 1], cc = c[3 * r + 2];
+                const bool own_from = r < 2;
+                const double sgn = own_from ? 1.0 : -1.0;
+                const double cross = bb * cs + sgn * cc * sn;
+                const int k0 = a.k_ohm + 20 * (int)l + 5 * r;
+                J(k0) = 1.0;
+                if (own_from) {
+                    J(k0 + 1) = -(2.0 * aa * vf + cross * vt);
+                    J(k0 + 2) = -(cross * vf);
+                } else {
+                    J(k0 + 1) = -(cross * vt);
+                    J(k0 + 2) = -(2.0 * aa * vt + cross * vf);
+                }
+                const double dd = vv * (-bb * sn + sgn * cc * cs);
+                J(k0 + 3) = -dd;
+                J(k0 + 4) = dd;
+            }
+        }
+    }
+}
+// one balance row per item (2 per bus: P, Q): affine entries in j_str order, shunt term, and their derivatives
+template <bool BATCH, bool TRIAL>
+__global__ void __launch_bounds__(kThreads) k_acopf_bus(AcopfDev a, AcopfIo io) {
+    Map<BATCH> mp;
+    const int B = io.B, s = mp.s;
+    for (int64_t r = mp.first; r < 2 * a.nb; r += mp.stride) {
+        const int bus = (int)(r >> 1), is_q = (int)(r & 1);
+        const double vm = acopf_x<TRIAL>(io, a.o_vm + bus, s);
+        double acc = 0.0;
+        for (int k = a.bal_ptr[r]; k < a.bal_ptr[r + 1]; ++k) {
+            const double cf = a.bal_coef[k];
+            const bool shunt = cf != cf;   // NaN marks the vm^2 slot
+            acc += (shunt ? 0.0 : cf) * acopf_x<TRIAL>(io, a.bal_col[k], s);
+            if (!TRIAL)
+                io.dE[(int64_t)(a.k_bal + k) * B + s] = shunt ? (is_q ? -2.0 * a.bs[bus] : 2.0 * a.gs[bus]) * vm : cf;
+        }
+        acc += is_q ? -(a.bs[bus] * vm * vm) : a.gs[bus] * vm * vm;
+        io.E[(int64_t)(a.r_bal + r) * B + s] = acc;
+    }
+}
+// objective, its gradient, reference-angle row and dc-line loss rows: one thread per scenario
+template <bool TRIAL>
+__global__ void k_acopf_misc(AcopfDev a, AcopfIo io, int n) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= io.B) return;
+    const int B = io.B;
+    double f = 0.0;
+    for (int k = 0; k < a.ng; ++k) {
+        const double pg = acopf_x<TRIAL>(io, a.o_pg + k, s);
+        f += a.cost2[k] * pg * pg + a.cost1[k] * pg + a.cost0[k];
+        if (!TRIAL) io.df[(int64_t)(a.o_pg + k) * B + s] = 2.0 * a.cost2[k] * pg + a.cost1[k];
+    }
+    io.f[s] = f;
+    io.E[(int64_t)a.r_ref * B + s] = acopf_x<TRIAL>(io, a.o_va + a.ref_bus, s);
+    if (!TRIAL) io.dE[(int64_t)a.k_ref * B + s] = 1.0;
+    for (int d = 0; d < a.nd; ++d) {
+        const double pf = acopf_x<TRIAL>(io, a.o_pdc + d, s), pt = acopf_x<TRIAL>(io, a.o_pdc + a.nd + d, s);
+        io.E[(int64_t)(a.r_dc + d) * B + s] = (1.0 - a.dc_loss1[d]) * pf + pt;
+        if (!TRIAL) {
+            io.dE[(int64_t)(a.k_dc + 2 * d) * B + s] = 1.0 - a.dc_loss1[d];
+            io.dE[(int64_t)(a.k_dc + 2 * d + 1) * B + s] = 1.0;
+        }
+    }
+}
+
 // =================================== host side: pattern analysis ================================================
 struct Pattern {
     int n = 0, m = 0;
@@ -381,6 +514,11 @@ struct SlpHandle {
     Pinned pin_small;
     int64_t own_launches = 0;
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+    // device-side ACOPF evaluator (optional)
+    bool has_acopf = false;
+    AcopfDev acopf;
+    DBuf<int> ac_f, ac_t, ac_bal_ptr, ac_bal_col;
+    DBuf<double> ac_coef, ac_gs, ac_bs, ac_c2, ac_c1, ac_c0, ac_loss1, ac_bal_coef, ac_ftrial;
 
     ~SlpHandle() {
         normal.reset();
@@ -1119,6 +1257,166 @@ int asm_slp_merit_derivative(asm_slp *hh, const double *nu, int32_t feasibility,
     ASM_TRY(h.finish_reduce(std::max(g.grid.x, gc.grid.x), 0u, r));
     for (int s = 0; s < h.Buser; ++s)
         out[s] = (feasibility ? r[s * R_COUNT + R_B] : r[s * R_COUNT + R_C]) - r[s * R_COUNT + R_A];
+    return ASM_OK;
+}
+
+// ---- device-side ACOPF evaluator ------------------------------------------------------------------------------
+int asm_slp_attach_acopf(asm_slp *hh, const asm_acopf_desc *d) {
+    SLP_GUARD();
+    (void)B;
+    if (!d || d->nb <= 0 || d->ng < 0 || d->nl < 0 || d->nd < 0) return fail(ASM_E_INVALID, "bad ACOPF description");
+    if (!d->f_bus || !d->t_bus || !d->coef || !d->gs || !d->bs || !d->cost2 || !d->cost1 || !d->cost0 || !d->bal_ptr ||
+        (d->nd > 0 && !d->dc_loss1))
+        return fail(ASM_E_INVALID, "null array in the ACOPF description");
+    AcopfDev a;
+    a.nb = d->nb; a.ng = d->ng; a.nl = d->nl; a.nd = d->nd; a.ref_bus = d->ref_bus;
+    a.nnz_bal = d->bal_ptr[2 * d->nb];
+    int o = 0;
+    a.o_va = o; o += a.nb;
+    a.o_vm = o; o += a.nb;
+    a.o_pg = o; o += a.ng;
+    a.o_qg = o; o += a.ng;
+    a.o_p = o; o += 2 * a.nl;
+    a.o_q = o; o += 2 * a.nl;
+    a.o_pdc = o; o += 2 * a.nd;
+    a.o_qdc = o; o += 2 * a.nd;
+    const int n = o;
+    int r = 0;
+    a.r_angmax = r; r += a.nl;
+    a.r_angmin = r; r += a.nl;
+    a.r_ref = r; r += 1;
+    a.r_dc = r; r += a.nd;
+    a.r_thermal = r; r += 2 * a.nl;
+    a.r_bal = r; r += 2 * a.nb;
+    a.r_ohm = r; r += 4 * a.nl;
+    const int m = r;
+    int k = 0;
+    a.k_angmax = k; k += 2 * a.nl;
+    a.k_angmin = k; k += 2 * a.nl;
+    a.k_ref = k; k += 1;
+    a.k_dc = k; k += 2 * a.nd;
+    a.k_thermal = k; k += 4 * a.nl;
+    a.k_bal = k; k += a.nnz_bal;
+    a.k_ohm = k; k += 20 * a.nl;
+    if (n != h.n || m != h.m || (int64_t)k != h.pat.nnz_coo)
+        return fail(ASM_E_INVALID, "ACOPF description does not match the handle's n, m, nnz (layout of examples/acopf.py)");
+    if (a.ref_bus < 0 || a.ref_bus >= a.nb) return fail(ASM_E_INVALID, "reference bus out of range");
+    for (int l = 0; l < a.nl; ++l)
+        if (d->f_bus[l] < 0 || d->f_bus[l] >= a.nb || d->t_bus[l] < 0 || d->t_bus[l] >= a.nb)
+            return fail(ASM_E_INVALID, "branch terminal out of range");
+    for (int t = 0; t < a.nnz_bal; ++t)
+        if (d->bal_col[t] < 0 || d->bal_col[t] >= n) return fail(ASM_E_INVALID, "balance column out of range");
+    auto upi = [&](DBuf<int> &b, const int32_t *src, size_t cnt) -> int {
+        ASM_TRY(b.alloc(std::max<size_t>(cnt, 1)));
+        if (cnt) ASM_CK(cudaMemcpy(b.p, src, cnt * sizeof(int), cudaMemcpyHostToDevice));
+        return ASM_OK;
+    };
+    auto upd = [&](DBuf<double> &b, const double *src, size_t cnt) -> int {
+        ASM_TRY(b.alloc(std::max<size_t>(cnt, 1)));
+        if (cnt) ASM_CK(cudaMemcpy(b.p, src, cnt * sizeof(double), cudaMemcpyHostToDevice));
+        return ASM_OK;
+    };
+    ASM_TRY(upi(h.ac_f, d->f_bus, a.nl));
+    ASM_TRY(upi(h.ac_t, d->t_bus, a.nl));
+    ASM_TRY(upi(h.ac_bal_ptr, d->bal_ptr, 2 * (size_t)a.nb + 1));
+    ASM_TRY(upi(h.ac_bal_col, d->bal_col, a.nnz_bal));
+    ASM_TRY(upd(h.ac_coef, d->coef, 12 * (size_t)a.nl));
+    ASM_TRY(upd(h.ac_gs, d->gs, a.nb));
+    ASM_TRY(upd(h.ac_bs, d->bs, a.nb));
+    ASM_TRY(upd(h.ac_c2, d->cost2, a.ng));
+    ASM_TRY(upd(h.ac_c1, d->cost1, a.ng));
+    ASM_TRY(upd(h.ac_c0, d->cost0, a.ng));
+    ASM_TRY(upd(h.ac_loss1, d->dc_loss1, a.nd));
+    ASM_TRY(upd(h.ac_bal_coef, d->bal_coef, a.nnz_bal));
+    ASM_TRY(h.ac_ftrial.alloc(h.B));
+    a.f_bus = h.ac_f.p; a.t_bus = h.ac_t.p; a.bal_ptr = h.ac_bal_ptr.p; a.bal_col = h.ac_bal_col.p;
+    a.coef = h.ac_coef.p; a.gs = h.ac_gs.p; a.bs = h.ac_bs.p; a.cost2 = h.ac_c2.p; a.cost1 = h.ac_c1.p;
+    a.cost0 = h.ac_c0.p; a.dc_loss1 = h.ac_loss1.p; a.bal_coef = h.ac_bal_coef.p;
+    h.acopf = a;
+    h.has_acopf = true;
+    return ASM_OK;
+}
+
+// eval_functions! on the device followed by the data push of sub_optimize!: x[batch][n], delta[batch]
+int asm_slp_eval_acopf(asm_slp *hh, const double *x, const double *delta, int32_t feasibility) {
+    SLP_GUARD();
+    if (!h.has_acopf) return fail(ASM_E_STATE, "asm_slp_attach_acopf first");
+    if (!x || !delta) return fail(ASM_E_INVALID, "null argument");
+    ASM_TRY(h.put(x, h.n, h.Buser, h.xk.p));
+    double *ps = (double *)h.pin_small.p;
+    for (int s = 0; s < B; ++s) ps[s] = delta[s < h.Buser ? s : 0];
+    ASM_CK(cudaMemcpyAsync(h.delta.p, ps, B * sizeof(double), cudaMemcpyHostToDevice, stream));
+    ASM_TRY(h.df.zero(stream));
+    AcopfIo io;
+    io.xk = h.xk.p; io.p = nullptr; io.alpha = nullptr;
+    io.f = h.fval.p; io.df = h.df.p; io.E = h.E.p; io.dE = h.dE.p; io.B = B;
+    const Geo gl = geo_for(std::max(h.acopf.nl, 1), B), gb = geo_for(2 * h.acopf.nb, B);
+    if (B > 1) {
+        k_acopf_branch<true, false><<<gl.grid, gl.block, 0, stream>>>(h.acopf, io);
+        k_acopf_bus<true, false><<<gb.grid, gb.block, 0, stream>>>(h.acopf, io);
+    } else {
+        k_acopf_branch<false, false><<<gl.grid, gl.block, 0, stream>>>(h.acopf, io);
+        k_acopf_bus<false, false><<<gb.grid, gb.block, 0, stream>>>(h.acopf, io);
+    }
+    k_acopf_misc<false><<<(B + 127) / 128, 128, 0, stream>>>(h.acopf, io, h.n);
+    own_launches += 3;
+    ASM_CK(cudaGetLastError());
+    return h.update_device(feasibility);
+}
+
+// the evaluation of the last asm_slp_eval_acopf / asm_slp_update, back on the host (tests, drivers): any may be NULL
+int asm_slp_get_eval(asm_slp *hh, double *f, double *df, double *E, double *dE) {
+    SLP_GUARD();
+    (void)B;
+    if (h.phase < 0) return fail(ASM_E_STATE, "no evaluation yet");
+    if (f) ASM_CK(cudaMemcpyAsync(f, h.fval.p, h.Buser * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    ASM_TRY(h.get(h.df.p, h.n, df));
+    ASM_TRY(h.get(h.E.p, h.m, E));
+    ASM_TRY(h.get(h.dE.p, h.pat.nnz_coo, dE));
+    ASM_CK(cudaStreamSynchronize(stream));
+    return ASM_OK;
+}
+
+// compute_phi(x + alpha p) (slp.jl:79-115) with g and f evaluated on the device at the trial point: x_k of the last
+// evaluation, p of the last solve.  base[batch] is only read in feasibility restoration (prim_infeas); otherwise the
+// base is f(x + alpha p).  out[batch].
+int asm_slp_acopf_trial(asm_slp *hh, const double *alpha, const double *nu, const double *base, int32_t feasibility,
+                        double *out) {
+    SLP_GUARD();
+    if (!h.has_acopf) return fail(ASM_E_STATE, "asm_slp_attach_acopf first");
+    if (!alpha || !nu || !out || (feasibility && !base)) return fail(ASM_E_INVALID, "null argument");
+    if (h.phase < 0 || !h.solved) return fail(ASM_E_STATE, "no solved sub-LP yet");
+    ASM_TRY(h.extract_device());
+    ASM_TRY(h.put(nu, h.m, h.Buser, h.tmp_m2.p));
+    double *ps = (double *)h.pin_small.p + (size_t)B * R_COUNT;
+    for (int s = 0; s < B; ++s) ps[s] = alpha[s < h.Buser ? s : 0];
+    ASM_CK(cudaMemcpyAsync(h.d_alpha.p, ps, sizeof(double) * B, cudaMemcpyHostToDevice, stream));
+    AcopfIo io;
+    io.xk = h.xk.p; io.p = h.p.p; io.alpha = h.d_alpha.p;
+    io.f = h.ac_ftrial.p; io.df = nullptr; io.E = h.tmp_m.p; io.dE = nullptr; io.B = B;
+    const Geo gl = geo_for(std::max(h.acopf.nl, 1), B), gb = geo_for(2 * h.acopf.nb, B);
+    if (B > 1) {
+        k_acopf_branch<true, true><<<gl.grid, gl.block, 0, stream>>>(h.acopf, io);
+        k_acopf_bus<true, true><<<gb.grid, gb.block, 0, stream>>>(h.acopf, io);
+    } else {
+        k_acopf_branch<false, true><<<gl.grid, gl.block, 0, stream>>>(h.acopf, io);
+        k_acopf_bus<false, true><<<gb.grid, gb.block, 0, stream>>>(h.acopf, io);
+    }
+    k_acopf_misc<true><<<(B + 127) / 128, 128, 0, stream>>>(h.acopf, io, h.n);
+    own_launches += 3;
+    SlpView sv = h.view();
+    const Geo g = geo_for(h.m, B);
+    SLP_KB(k_merit, g, sv, (const double *)h.tmp_m.p, h.tmp_m2.p, h.pslack.p, (const double *)h.d_alpha.p, (int)feasibility,
+           h.partials.p);
+    std::vector<double> r;
+    ASM_TRY(h.finish_reduce(g.grid.x, 0u, r));
+    std::vector<double> ft(B, 0.0);
+    ASM_CK(cudaMemcpyAsync(ft.data(), h.ac_ftrial.p, sizeof(double) * B, cudaMemcpyDeviceToHost, stream));
+    ASM_CK(cudaStreamSynchronize(stream));
+    for (int s = 0; s < h.Buser; ++s) {
+        const double b0 = feasibility ? base[s] + alpha[s] * r[s * R_COUNT + R_B] : ft[s];
+        out[s] = b0 + r[s * R_COUNT + R_A];
+    }
     return ASM_OK;
 }
 

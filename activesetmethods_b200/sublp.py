@@ -231,6 +231,52 @@ class SubLp:
         capi.check(self._lib.asm_slp_engine_info(self._h, C.byref(e), C.byref(g), C.byref(k)))
         return dict(engine=e.value, group_size=g.value, groups=k.value)
 
+    # -- device-side ACOPF evaluator ----------------------------------------------------------
+    def attach_acopf(self, model):
+        """Hand the network of an ``examples.acopf.AcopfModel`` to the device so that ``eval_acopf`` /
+        ``acopf_trial`` replace the host callbacks (``src/MOI_wrapper.jl:1047-1069``).  All scenarios of the batch
+        share the network; loads only enter the row bounds given at construction."""
+        net = model.net
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)   # noqa: E731
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)  # noqa: E731
+        cf = model._cf
+        keep = dict(
+            f_bus=i32(net.f_bus), t_bus=i32(net.t_bus),
+            coef=f64(np.stack([cf[k] for k in ("a_pf", "b_pf", "c_pf", "a_qf", "b_qf", "c_qf", "a_pt", "b_pt", "c_pt",
+                                               "a_qt", "b_qt", "c_qt")])),
+            gs=f64(net.gs), bs=f64(net.bs), cost2=f64(net.cost2), cost1=f64(net.cost1), cost0=f64(net.cost0),
+            dc_loss1=f64(net.dc_loss1 if model.nd else np.zeros(1)),
+            bal_ptr=i32(np.concatenate([[0], np.cumsum(np.bincount(model._bal_rows - model.r_bal,
+                                                                   minlength=2 * model.nb))])),
+            bal_col=i32(model._bal_cols), bal_coef=f64(model._bal_coef))
+        d = capi.AcopfDesc()
+        d.nb, d.ng, d.nl, d.nd, d.ref_bus = model.nb, model.ng, model.nl, model.nd, int(net.ref_bus)
+        for k, a in keep.items():
+            setattr(d, k, a.ctypes.data_as(capi.c_int32_p if a.dtype == np.int32 else capi.c_double_p))
+        capi.check(self._lib.asm_slp_attach_acopf(self._h, C.byref(d)))
+
+    def eval_acopf(self, x, delta=1000.0, feasibility=False):
+        """``eval_functions!`` (slp.jl:186-191) on the device at ``x`` + the device part of ``update``."""
+        capi.check(self._lib.asm_slp_eval_acopf(self._h, capi.dptr(self._vec(x, self.n)), capi.dptr(self._scal(delta)),
+                                                1 if feasibility else 0))
+
+    def get_eval(self):
+        """(f, df, E, dE) of the last evaluation, ``[batch, ...]`` (squeezed when ``batch == 1``)."""
+        B = self.batch
+        f = np.empty(B); df = np.empty((B, self.n)); E = np.empty((B, self.m)); dE = np.empty((B, self.nnz_coo))
+        capi.check(self._lib.asm_slp_get_eval(self._h, capi.dptr(f), capi.dptr(df), capi.dptr(E), capi.dptr(dE)))
+        if B == 1 and self._squeeze:
+            return float(f[0]), df[0], E[0], dE[0]
+        return f, df, E, dE
+
+    def acopf_trial(self, alpha, nu, base=None, feasibility=False):
+        """``compute_phi(x + alpha p)`` (slp.jl:79-115) with f and g evaluated on the device at the trial point."""
+        out = np.empty(self.batch)
+        capi.check(self._lib.asm_slp_acopf_trial(
+            self._h, capi.dptr(self._scal(alpha)), capi.dptr(self._vec(nu, self.m)),
+            capi.dptr(None if base is None else self._scal(base)), 1 if feasibility else 0, capi.dptr(out)))
+        return self._ret(out) if self._squeeze else out
+
     # -- instrumentation ----------------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self._lib.asm_slp_launch_count(self._h))

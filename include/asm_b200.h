@@ -195,6 +195,33 @@ int asm_slp_merit_phi(asm_slp *h, const double *base, const double *E_trial, con
 /* compute_derivative (slp.jl:122-147) with the df, E of the last update and the p / slacks of the last solve */
 int asm_slp_merit_derivative(asm_slp *h, const double *nu, int32_t feasibility, double *out);
 
+/* ---- device-side ACOPF evaluator ------------------------------------------------------
+ * The role of the NLPEvaluator callbacks (src/MOI_wrapper.jl:1047-1069) and of eval_functions!
+ * (src/algorithms/slp.jl:186-191) for the ACP-polar OPF in the variable / row / Jacobian layout of
+ * activesetmethods_b200/examples/acopf.py: variables va[nb] vm[nb] pg[ng] qg[ng] p[2nl] q[2nl] pdc[2nd] qdc[2nd];
+ * rows angmax[nl] angmin[nl] ref dc[nd] thermal[2nl] balance[2nb] ohm[4nl]; j_str in the same block order.
+ * All scenarios of a batch share the network (loads only enter the row bounds). */
+typedef struct asm_acopf_desc {
+    int32_t nb, ng, nl, nd, ref_bus;
+    const int32_t *f_bus, *t_bus;         /* [nl] 0-based bus indices                                              */
+    const double *coef;                   /* [12][nl]: a, b, c of p_fr, q_fr, p_to, q_to (acopf.py `_cf` order)     */
+    const double *gs, *bs;                /* [nb] shunts                                                           */
+    const double *cost2, *cost1, *cost0;  /* [ng]                                                                  */
+    const double *dc_loss1;               /* [nd] (may be NULL when nd = 0)                                        */
+    const int32_t *bal_ptr;               /* [2nb + 1] CSR over the balance rows of their entries in j_str order   */
+    const int32_t *bal_col;               /* [bal_ptr[2nb]] 0-based columns                                        */
+    const double *bal_coef;               /* constant coefficients, NaN at the vm^2 (shunt) slots                  */
+} asm_acopf_desc;
+int asm_slp_attach_acopf(asm_slp *h, const asm_acopf_desc *d);
+/* eval_functions! on the device at x[batch][n], then the device part of asm_slp_update */
+int asm_slp_eval_acopf(asm_slp *h, const double *x, const double *delta, int32_t feasibility);
+/* f[batch], df[batch][n], E[batch][m], dE[batch][nnz_coo] of the last evaluation; any pointer may be NULL */
+int asm_slp_get_eval(asm_slp *h, double *f, double *df, double *E, double *dE);
+/* compute_phi(x + alpha p) (slp.jl:79-115; the backtracking of slp_line_search.jl:228-241) with f and g evaluated on
+ * the device at the trial point; `base` (prim_infeas) is read in feasibility restoration only */
+int asm_slp_acopf_trial(asm_slp *h, const double *alpha, const double *nu, const double *base, int32_t feasibility,
+                        double *out);
+
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 /* kernels launched by this handle's solver since creation (all of them this library's own) */
 int64_t asm_slp_launch_count(asm_slp *h);
