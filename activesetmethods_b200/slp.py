@@ -443,9 +443,14 @@ class SlpLSBatch:
     one `update`, the KKT reductions, one sub-LP batch solve (two when some scenarios are in feasibility
     restoration), and one batched merit evaluation per backtracking round.  Per scenario the control flow is
     exactly ``SlpLS.run`` (reference ``slp_line_search.jl:78-215``) — a scenario that terminates simply stops
-    moving while the others go on.  ``problems`` are objects with the ``Model.from_problem`` interface."""
+    moving while the others go on.  ``problems`` are objects with the ``Model.from_problem`` interface.
 
-    def __init__(self, problems, parameters: Parameters | None = None):
+    ``device_evaluator=True`` (ACOPF scenarios of one network, B200 engine): the NLP callbacks are not called at all —
+    f, g and the Jacobian are evaluated by the device-side ACOPF evaluator (``SubLp.eval_acopf``) and every
+    backtracking trial is one ``SubLp.acopf_trial`` call for the whole batch."""
+
+    def __init__(self, problems, parameters: Parameters | None = None, device_evaluator: bool = False):
+        self.device_evaluator = bool(device_evaluator)
         self.problems = list(problems)
         self.options = parameters if parameters is not None else Parameters()
         p0 = self.problems[0]
@@ -485,7 +490,11 @@ class SlpLSBatch:
             opt = SubLp(self.n, self.m, prs[0].j_str, arr("x_L"), arr("x_U"), arr("g_L"), arr("g_U"), batch=self.B,
                         device=o.device, **{"warm_start": 1, **o.lp_options})
             opt._squeeze = False
+            if self.device_evaluator:
+                opt.attach_acopf(prs[0])
             return opt
+        if self.device_evaluator:
+            raise ValueError("device_evaluator needs the B200 engine")
         return o.external_optimizer(self.n, self.m, prs[0].j_str, arr("x_L"), arr("x_U"), arr("g_L"), arr("g_U"),
                                     batch=self.B)
 
@@ -500,7 +509,9 @@ class SlpLSBatch:
         """Sub-LP batch of one phase; returns the extract tuple plus phi(0) and the directional derivative computed
         while the device still holds this phase's step and slacks."""
         opt = self.optimizer
-        if fr:                      # the normal-phase data push was done for the KKT metrics of this round
+        if fr and self.device_evaluator:
+            opt.eval_acopf(self.x, 1000.0, True)
+        elif fr:                    # the normal-phase data push was done for the KKT metrics of this round
             opt.update(self.x, self.f, self.df, self.E, self.dE, 1000.0, True)
         p, lam, mu_u, mu_l, slack, status = opt.solve_extract()
         info = getattr(opt, "last_info", None) or []
@@ -521,10 +532,14 @@ class SlpLSBatch:
         while self.running.any():
             self.rounds += 1
             run = np.nonzero(self.running)[0]
-            for s in run:
-                self._eval(s)
             # KKT metrics with last round's multipliers on this round's Jacobian (App. C-7)
-            opt.update(self.x, self.f, self.df, self.E, self.dE, 1000.0, False)
+            if self.device_evaluator:
+                opt.eval_acopf(self.x, 1000.0, False)
+                self.f[:] = opt.get_eval_f()
+            else:
+                for s in run:
+                    self._eval(s)
+                opt.update(self.x, self.f, self.df, self.E, self.dE, 1000.0, False)
             self.prim_infeas[run] = np.atleast_1d(opt.norm_violations(None, None, INF))[run]
             self.dual_infeas[run] = np.atleast_1d(opt.kt_residuals(self.lam, self.mult_x_U, self.mult_x_L))[run]
             self.compl[run] = np.atleast_1d(opt.norm_complementarity(self.lam))[run]
@@ -609,12 +624,15 @@ class SlpLSBatch:
         Et = self.E.copy()
         while searching.any():
             act = np.nonzero(searching)[0]
-            for s in act:
-                pr = self.problems[s]
-                xt = self.x[s] + self.alpha[s] * self.p[s]
-                pr.eval_g(xt, Et[s])
-                base[s] = self.prim_infeas[s] if fr else pr.eval_f(xt)
-            phi = np.atleast_1d(self.optimizer.merit_phi(base, Et, self.nu, self.alpha, fr))
+            if self.device_evaluator:
+                phi = np.atleast_1d(self.optimizer.acopf_trial(self.alpha, self.nu, self.prim_infeas if fr else None, fr))
+            else:
+                for s in act:
+                    pr = self.problems[s]
+                    xt = self.x[s] + self.alpha[s] * self.p[s]
+                    pr.eval_g(xt, Et[s])
+                    base[s] = self.prim_infeas[s] if fr else pr.eval_f(xt)
+                phi = np.atleast_1d(self.optimizer.merit_phi(base, Et, self.nu, self.alpha, fr))
             for s in act:
                 if phi[s] > phi0[s] + o.eta * self.alpha[s] * deriv[s]:
                     if self.alpha[s] < o.min_alpha:

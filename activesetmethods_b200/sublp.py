@@ -260,6 +260,12 @@ class SubLp:
         capi.check(self._lib.asm_slp_eval_acopf(self._h, capi.dptr(self._vec(x, self.n)), capi.dptr(self._scal(delta)),
                                                 1 if feasibility else 0))
 
+    def get_eval_f(self):
+        """f[batch] of the last evaluation (the only piece the batched driver needs back on the host)."""
+        f = np.empty(self.batch)
+        capi.check(self._lib.asm_slp_get_eval(self._h, capi.dptr(f), None, None, None))
+        return f
+
     def get_eval(self):
         """(f, df, E, dE) of the last evaluation, ``[batch, ...]`` (squeezed when ``batch == 1``)."""
         B = self.batch

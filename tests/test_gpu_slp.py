@@ -107,6 +107,22 @@ def test_batched_scenarios_line_search(gpu):
         assert abs(batch.obj_val[k] - ref.obj_val) <= 1e-2 * abs(ref.obj_val), (s, batch.obj_val[k], ref.obj_val)
 
 
+def test_batched_scenarios_device_evaluator(gpu):
+    """The same batch with the NLP callbacks replaced by the device-side ACOPF evaluator (no host evaluation in the
+    loop, backtracking trials evaluated on the device): same statuses and SLP iteration counts as the host-evaluator
+    run, objectives equal to 1e-6."""
+    from activesetmethods_b200.slp import Parameters, SlpLSBatch
+    net = acopf.case9()
+    ids = [1, 2, 3, 4, 5, 6]
+    host = SlpLSBatch([acopf.AcopfModel(acopf.perturb_loads(net, s)) for s in ids],
+                      Parameters(max_iter=100, lp_options=LP)).run()
+    dev = SlpLSBatch([acopf.AcopfModel(acopf.perturb_loads(net, s)) for s in ids],
+                     Parameters(max_iter=100, lp_options=LP), device_evaluator=True).run()
+    assert np.array_equal(dev.ret, host.ret) and np.all(np.isin(dev.ret, (0, 6)))
+    assert np.array_equal(dev.iter, host.iter)
+    assert np.all(np.abs(dev.obj_val - host.obj_val) <= 1e-6 * np.abs(host.obj_val))
+
+
 def test_missing_external_optimizer(gpu):
     """model.jl:64-66: no external optimizer -> Invalid_Option (-12)."""
     from activesetmethods_b200.slp import Model, Parameters, optimize
