@@ -14,7 +14,7 @@ for kv in sys.argv[3:]:
     opts[k] = float(v) if ("." in v or "e" in v) else int(v)
 net = bench.network(case)
 mdl, d = bench.linearise(net, [1 + s for s in range(S)])
-lp = SubLp(mdl.n, mdl.m, mdl.j_str, d["xL"], d["xU"], d["gL"], d["gU"], batch=S, eps_rel=1e-6, **opts)
+lp = SubLp(mdl.n, mdl.m, mdl.j_str, d["xL"], d["xU"], d["gL"], d["gU"], batch=S, **{"eps_rel": 1e-6, **opts})
 lp.sub_optimize(d["x"], d["f"], d["df"], d["E"], d["dE"], 1000.0, False)
 its = np.array([i["iterations"] for i in lp.last_info]); st = np.array([i["status"] for i in lp.last_info])
 order = np.argsort(-its)
