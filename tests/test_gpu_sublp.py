@@ -102,6 +102,59 @@ def test_numerically_empty_rows_do_not_stall(gpu):
     lp.close()
 
 
+@pytest.mark.parametrize("B", [1, 3])
+def test_metric_reductions_match_oracle(gpu, B):
+    """The device reductions of the iteration — norm_violations (common.jl:75-98, p = 1, 2, inf), KT_residuals
+    (:35-44), norm_complementarity (:51-68), the row norms of compute_nu! (slp.jl:54-66), compute_phi (slp.jl:79-115)
+    in both phases and compute_derivative (slp.jl:122-147) — against the oracle's functions at random points."""
+    from activesetmethods_b200.sublp import SubLp
+    pr = problem("case9")
+    rng = np.random.default_rng(B)
+    x = rng.uniform(np.where(np.isfinite(pr.x_L), pr.x_L, -0.3) - 0.05, np.where(np.isfinite(pr.x_U), pr.x_U, 0.3) + 0.05,
+                    (B, pr.n))
+    f = np.array([pr.eval_f(xx) for xx in x])
+    df = np.array([pr.eval_grad_f(xx, np.zeros(pr.n)) for xx in x])
+    E = np.array([pr.eval_g(xx, np.zeros(pr.m)) for xx in x])
+    dE = np.array([pr.eval_jac_g(xx, "eval", None, None, np.zeros(len(pr.j_str))) for xx in x])
+    lam = rng.standard_normal((B, pr.m)); mu_u = -rng.random((B, pr.n)); mu_l = rng.random((B, pr.n))
+    nu = rng.random((B, pr.m)) * 3.0
+    pat = so.JacobianPattern(pr.m, pr.n, pr.j_str)
+    lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, batch=B, eps_rel=1e-8)
+    lp._squeeze = False
+    close = lambda a, b: np.allclose(np.ravel(a), np.ravel(b), rtol=1e-12, atol=1e-13)   # noqa: E731
+    for fr in (False, True):
+        lp.update(x, f, df, E, dE, 1000.0, fr)
+        for pn in (1, 2, np.inf):
+            assert close(lp.norm_violations(None, None, pn),
+                         [so.norm_violations(E[s], pr.g_L, pr.g_U, x[s], pr.x_L, pr.x_U, pn) for s in range(B)])
+        J = [pat.matrix(pat.assemble(dE[s])) for s in range(B)]
+        assert close(lp.kt_residuals(lam, mu_u, mu_l), [so.kt_residuals(df[s], lam[s], mu_u[s], mu_l[s], J[s]) for s in range(B)])
+        assert close(lp.norm_complementarity(lam), [so.norm_complementarity(E[s], pr.g_L, pr.g_U, lam[s]) for s in range(B)])
+        assert close(lp.row_norms(), [so.row_norms(J[s]) for s in range(B)])
+        p, lam_lp, _, _, slack, status = lp.solve_extract()
+        if not np.all(np.atleast_1d(status) == 0):
+            assert not fr      # a random point may make the normal-phase LP infeasible; the elastic one never is
+            continue
+        slack = np.asarray(slack).reshape(B, pr.m, 2)
+        # the oracle's drivers hold the same formulas: drive one of its objects with this data
+        for s in range(B):
+            o = so.SlpLS(problem("case9"), so.Parameters())
+            o.x, o.f, o.df, o.E, o.dE = x[s].copy(), f[s], df[s].copy(), E[s].copy(), dE[s].copy()
+            o.p, o.p_slack, o.nu, o.feasibility_restoration = np.atleast_2d(p)[s], slack[s], nu[s], fr
+            o.prim_infeas = 0.37
+            alpha = 0.6
+            Et = pr.eval_g(x[s] + alpha * o.p, np.zeros(pr.m))
+            base = 0.37 if fr else pr.eval_f(x[s] + alpha * o.p)
+            Ets = np.tile(Et, (B, 1)); bases = np.full(B, base); alphas = np.full(B, alpha)
+            got = np.atleast_1d(lp.merit_phi(bases, Ets, nu, alphas, fr))[s]
+            assert abs(got - o.compute_phi(x[s], alpha, o.p)) <= 1e-10 * max(1.0, abs(got)), (fr, s)
+            got0 = np.atleast_1d(lp.merit_phi(np.full(B, 0.37 if fr else f[s]), None, nu, np.zeros(B), fr))[s]
+            assert abs(got0 - o.compute_phi(x[s], 0.0, o.p)) <= 1e-10 * max(1.0, abs(got0)), (fr, s)
+            gotd = np.atleast_1d(lp.merit_derivative(nu, fr))[s]
+            assert abs(gotd - o.compute_derivative()) <= 1e-9 * max(1.0, abs(gotd)), (fr, s)
+    lp.close()
+
+
 def test_assembly_bit_exact_with_duplicates(gpu):
     """common.jl:12-20 with duplicate COO entries, wide dynamic range, signed zeros; batch of 40 scenarios."""
     from activesetmethods_b200.examples import small_nlps
