@@ -65,6 +65,9 @@ class Parameters:
     # engine options forwarded to asm_lp_params (not in the reference)
     lp_options: dict = field(default_factory=dict)
     device: int = 0
+    # line search on an examples.acopf.AcopfModel with the B200 engine: evaluate f, g, the Jacobian and the
+    # backtracking trials with the device-side ACOPF evaluator instead of the host callbacks
+    device_evaluator: bool = False
 
 
 class Model:
@@ -93,8 +96,10 @@ class Model:
     @classmethod
     def from_problem(cls, problem, parameters=None):
         """Wrap an object exposing ``n, m, x_L, x_U, g_L, g_U, j_str, x0`` and the four callbacks."""
-        return cls(problem.n, problem.m, problem.x_L, problem.x_U, problem.g_L, problem.g_U, problem.j_str,
-                   problem.eval_f, problem.eval_g, problem.eval_grad_f, problem.eval_jac_g, parameters, problem.x0)
+        mdl = cls(problem.n, problem.m, problem.x_L, problem.x_U, problem.g_L, problem.g_U, problem.j_str,
+                  problem.eval_f, problem.eval_g, problem.eval_grad_f, problem.eval_jac_g, parameters, problem.x0)
+        mdl.source = problem         # the device-side evaluator needs the network behind the callbacks
+        return mdl
 
     def add_statistic(self, name, value):                                   # model.jl:82-97
         if self.parameters.StatisticsFlag:
@@ -199,11 +204,15 @@ class _Slp:
     # slp.jl:79-115 — f / g at the trial point on the host (NLP evaluator), the m-length reduction on the GPU
     def compute_phi(self, x, alpha, p):
         pr = self.problem
+        if self.options.device_evaluator and alpha != 0.0:      # f and g at the trial point on the device
+            return self.optimizer.acopf_trial(alpha, self.nu, self.prim_infeas if self.feasibility_restoration else None,
+                                              self.feasibility_restoration)
         xp = x + alpha * p
         E = None if alpha == 0.0 else pr.eval_g(xp, np.zeros(pr.m))
         if self.feasibility_restoration:
             return self.optimizer.merit_phi(self.prim_infeas, E, self.nu, alpha, True)
-        return self.optimizer.merit_phi(pr.eval_f(xp), E, self.nu, alpha, False)
+        base = self.f if (self.options.device_evaluator and alpha == 0.0) else pr.eval_f(xp)
+        return self.optimizer.merit_phi(base, E, self.nu, alpha, False)
 
     # slp.jl:122-147
     def compute_derivative(self):
@@ -229,6 +238,8 @@ class _Slp:
         pr.obj_val = pr.eval_f(self.x)
         pr.status = int(self.ret)
         pr.x[:] = self.x
+        if self.options.device_evaluator:      # the loop kept g on the device: one host evaluation for the write-back
+            pr.eval_g(self.x, self.E)
         pr.g[:] = self.E
         pr.mult_g[:] = self.lam
         pr.mult_x_U[:] = self.mult_x_U
@@ -283,12 +294,19 @@ class SlpLS(_Slp):
         self.iter = 1
         if self.optimizer is None:
             self.optimizer = self._instantiate()
+        dev_eval = bool(o.device_evaluator)
+        if dev_eval:
+            self.optimizer.attach_acopf(self.problem.source)
         while True:
-            self.eval_functions()
             self.alpha = 0.0
             # KKT metrics with the multipliers of the previous iteration (App. C-7); they need the
             # Jacobian of *this* iterate on the device, which the update below provides
-            self.optimizer.update(self.x, self.f, self.df, self.E, self.dE, 1000.0, self.feasibility_restoration)
+            if dev_eval:
+                self.optimizer.eval_acopf(self.x, 1000.0, self.feasibility_restoration)
+                self.f = float(np.atleast_1d(self.optimizer.get_eval_f())[0])
+            else:
+                self.eval_functions()
+                self.optimizer.update(self.x, self.f, self.df, self.E, self.dE, 1000.0, self.feasibility_restoration)
             self.prim_infeas = self.optimizer.norm_violations(None, None, INF)
             self.dual_infeas = self.kt_residuals()
             self.compl = self.norm_complementarity()

@@ -123,6 +123,17 @@ def test_batched_scenarios_device_evaluator(gpu):
     assert np.all(np.abs(dev.obj_val - host.obj_val) <= 1e-6 * np.abs(host.obj_val))
 
 
+def test_line_search_on_device_evaluator(gpu):
+    """SlpLS on case9 with the NLP callbacks replaced by the device-side evaluator: same status, iteration count
+    and objective (1e-6) as the host-callback run, and the finish step's E / obj come out right."""
+    from activesetmethods_b200.slp import Model, Parameters, SlpLS
+    host = SlpLS(Model.from_problem(acopf.AcopfModel(acopf.case9()), Parameters(max_iter=100, lp_options=LP))).run()
+    dev = SlpLS(Model.from_problem(acopf.AcopfModel(acopf.case9()),
+                                   Parameters(max_iter=100, lp_options=LP, device_evaluator=True))).run()
+    assert dev.ret == host.ret == 0 and dev.iter == host.iter
+    assert abs(dev.obj_val - host.obj_val) <= 1e-6 * abs(host.obj_val)
+
+
 def test_missing_external_optimizer(gpu):
     """model.jl:64-66: no external optimizer -> Invalid_Option (-12)."""
     from activesetmethods_b200.slp import Model, Parameters, optimize
