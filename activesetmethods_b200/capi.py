@@ -30,6 +30,7 @@ class LpParams(C.Structure):
         ("pid_kp", C.c_double), ("pid_ki", C.c_double), ("pid_kd", C.c_double),
         ("engine", C.c_int32), ("group_size", C.c_int32),
         ("hand_over", C.c_double), ("weight_balance", C.c_double), ("tiny_rel", C.c_double),
+        ("ipm_max_iter", C.c_int32), ("ipm_refine", C.c_int32), ("ipm_reg", C.c_double), ("ipm_prox", C.c_double),
     ]
 
 

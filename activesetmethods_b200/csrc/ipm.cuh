@@ -1,0 +1,905 @@
+// Batched primal-dual barrier engine for   min c'x  s.t.  rl <= Kx <= ru,  lb <= x <= ub   on sm_100a.
+//
+// Stands where GLPK's simplex stands in the reference (MOI.optimize!(qp.model),
+// /root/reference/src/algorithms/subproblem.jl:490), next to the PDHG engines of lp_solver.cuh: measured on the SLP
+// sub-LPs of ACOPF (profiles/), first-order iterations cost 1e5 - 1e6 passes over the matrix per LP because the
+// linearised power-flow equations are an ill-conditioned, almost square equality system; a barrier method needs
+// 20 - 40 Newton steps, and every Newton step of every LP of a batch and of every SLP iteration factorises a matrix
+// with the SAME sparsity pattern (the Jacobian pattern is uploaded once, src/model.jl:10).  So:
+//   * symbolic work once per handle on the host (kkt_symbolic.hpp): ordering, pattern of L, level schedule, the
+//     list of products behind every entry of L;
+//   * numeric L D L' of the quasi-definite system  [-(Dx + d) K'; K (Ew + d)]  on the device, one independent dot
+//     product per entry of L (k_ldl_factor), scenarios across the lanes of a warp (element-major v[i * B + s]:
+//     index loads are warp-uniform, value loads coalesced), no pivoting, no atomics, bit-reproducible;
+//   * level-scheduled substitutions (k_ldl_fwd / k_ldl_bwd) and iterative refinement against the unregularised
+//     matrix (k_kkt_res_*);
+//   * Mehrotra predictor-corrector with every scalar decision taken on the device per scenario (k_ipm_decide,
+//     k_ipm_scalars); the host enqueues a fixed kernel sequence per Newton step and reads one 4-byte counter.
+// A small proximal term (q/2)|x|^2 selects the least-norm optimal step among the minimisers (restoration LPs,
+// min sum of slacks, always have a face of them); q is sized so that the dual residual it leaves in the LP stays
+// below ipm_prox * (1 + |c|).  Variables that end strictly complementary on a bound are returned exactly on it, as a
+// simplex code does: the reference compares them with == (subproblem.jl:522-529).
+// Algorithm: textbook (Mehrotra 1992; Vanderbei's quasi-definite systems) -- nothing here comes from the reference.
+#pragma once
+#include "kkt_symbolic.hpp"
+
+namespace asmb {
+
+enum {
+    I_RDX2 = 0,  // |rdx|^2 unscaled (proximal system)
+    I_RLP2,      // |c - K'y - z|^2 unscaled (the LP's own dual residual)
+    I_POBJ,      // sum cs x
+    I_QT,        // 1/2 sum Q x^2
+    I_DOBJC,     // l'zl - u'zu (+ fixed columns)
+    I_MUC,       // complementarity products of the columns
+    I_XN2,       // |x|^2 unscaled
+    I_RAYC,      // Farkas: box support of -(K'y)
+    I_KTY,       // max |(K'y)_j / dc_j|
+    I_RP2,       // |Kx - w|^2 unscaled
+    I_RDW2,      // |y - zl + zu|^2 unscaled
+    I_DOBJR,     // row part of the dual objective
+    I_MUR,       // complementarity products of the rows
+    I_RAYR,      // Farkas: rl'y+ + ru'y-
+    I_YMAX,      // max |y_i dr_i|
+    I_COUNT
+};
+// slots reused inside a Newton step (the residual slots are consumed by k_ipm_decide before)
+enum { J_AP = 0, J_AD, J_MUC, J_MUR, J_AP_R, J_AD_R };
+
+struct IpmState {
+    double mu, smu, ap, ad, qs, q_un;
+    int ncomp, hits, save, bad;
+};
+
+struct KktDev {
+    const KktTerm *terms;
+    const int *fchunk, *fstep;
+    const KktFwdItem *fwd;
+    const int *wchunk, *wstep;
+    const KktBwdItem *bwd;
+    const int *bstep;
+    const int *perm, *inv, *kmap;
+    double *W, *invd, *diag0;
+    int nnzL, N;
+};
+
+struct IpmView {
+    // columns
+    double *x, *zlx, *zux, *rdx, *Dx, *dzlx, *dzux, *clx, *cux;
+    // rows
+    double *w, *y, *zlw, *zuw, *rp, *rdw, *Ew, *dw, *dzlw, *dzuw, *clw, *cuw;
+    // KKT vectors (node order: columns then rows)
+    double *rhs0, *sol, *work;
+    IpmState *ist;
+    double delta, prox, eps;
+    int extra_hits, verbose;
+};
+
+__device__ __forceinline__ bool ipm_fin(double v) { return fabs(v) < 1.79e308; }
+
+// =================================== numeric L D L' ============================================================
+// Step l applies the updates of the columns of level l to their targets (fan-out).  A chunk = the terms of one target
+// in this step; BATCH: a warp owns a chunk and its lanes are 32 scenarios (index loads warp-uniform, value loads
+// coalesced); single LP: a thread owns a chunk.  Exactly one thread writes a target in a step and the terms of a
+// chunk are added in ascending k: bit-reproducible.  FUSED: gridDim.x == 1 and the block walks the steps [l0, l1)
+// with a barrier in between (W, invd and diag0 are read and written by the same kernel: plain loads).
+template <bool BATCH, bool FUSED>
+__global__ void __launch_bounds__(kThreads) k_ldl_factor(KktDev d, int B, int l0, int l1, const ScenState *st) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = BATCH ? blockIdx.y * 32 + lane : 0;
+    const bool live = st[s].status < 0;
+    const int first = BATCH ? blockIdx.x * kWarps + warp : blockIdx.x * kThreads + threadIdx.x;
+    const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
+    for (int l = l0; l < l1; ++l) {
+        const int c1 = d.fstep[l + 1];
+        if (live)
+            for (int c = d.fstep[l] + first; c < c1; c += stride) {
+                int q = d.fchunk[c];
+                const int q1 = d.fchunk[c + 1];
+                KktTerm u = d.terms[q];
+                const bool last = u.t & kLastBit;
+                const int t = u.t & ~kLastBit;
+                double acc = d.W[(int64_t)u.a * B + s] * d.W[(int64_t)u.b * B + s] * d.invd[(int64_t)u.k * B + s];
+                for (++q; q < q1; ++q) {
+                    u = d.terms[q];
+                    acc += d.W[(int64_t)u.a * B + s] * d.W[(int64_t)u.b * B + s] * d.invd[(int64_t)u.k * B + s];
+                }
+                if (t >= d.nnzL) {
+                    const int64_t e = (int64_t)(t - d.nnzL) * B + s;
+                    const double piv = d.diag0[e] - acc;
+                    d.diag0[e] = piv;
+                    if (last) d.invd[e] = 1.0 / piv;
+                } else {
+                    d.W[(int64_t)t * B + s] -= acc;
+                }
+            }
+        if (FUSED) __syncthreads();
+    }
+}
+
+// forward substitution  v <- L^-1 v  (fan-out, chunked like the factorisation; v indexed by node id, in place)
+template <bool BATCH, bool FUSED>
+__global__ void __launch_bounds__(kThreads) k_ldl_fwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = BATCH ? blockIdx.y * 32 + lane : 0;
+    const bool live = st[s].status < 0;
+    const int first = BATCH ? blockIdx.x * kWarps + warp : blockIdx.x * kThreads + threadIdx.x;
+    const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
+    for (int l = l0; l < l1; ++l) {
+        const int c1 = d.wstep[l + 1];
+        if (live)
+            for (int c = d.wstep[l] + first; c < c1; c += stride) {
+                int q = d.wchunk[c];
+                const int q1 = d.wchunk[c + 1];
+                KktFwdItem u = d.fwd[q];
+                const int dst = u.dst;
+                double acc = d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s] * d.invd[(int64_t)u.k * B + s];
+                for (++q; q < q1; ++q) {
+                    u = d.fwd[q];
+                    acc += d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s] * d.invd[(int64_t)u.k * B + s];
+                }
+                v[(int64_t)dst * B + s] -= acc;
+            }
+        if (FUSED) __syncthreads();
+    }
+}
+// v <- D^-1 v
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ldl_diag(KktDev d, double *v, int B, const ScenState *st) {
+    Map<BATCH> mp;
+    if (st[mp.s].status >= 0) return;
+    for (int64_t k = mp.first; k < d.N; k += mp.stride) v[(int64_t)d.perm[k] * B + mp.s] *= d.invd[k * B + mp.s];
+}
+// backward substitution  v <- L'^-1 v : the rows of a column are its ancestors in the elimination tree and sit on
+// distinct levels, so every item of a step has its own target; steps are walked downwards
+template <bool BATCH, bool FUSED>
+__global__ void __launch_bounds__(kThreads) k_ldl_bwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = BATCH ? blockIdx.y * 32 + lane : 0;
+    const bool live = st[s].status < 0;
+    const int first = BATCH ? blockIdx.x * kWarps + warp : blockIdx.x * kThreads + threadIdx.x;
+    const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
+    for (int l = l1 - 1; l >= l0; --l) {
+        const int q1 = d.bstep[l + 1];
+        if (live)
+            for (int q = d.bstep[l] + first; q < q1; q += stride) {
+                const KktBwdItem u = d.bwd[q];
+                v[(int64_t)u.dst * B + s] -=
+                    d.invd[(int64_t)u.k * B + s] * d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s];
+            }
+        if (FUSED) __syncthreads();
+    }
+}
+
+// assembled lower triangle: the scaled Jacobian values at their place in L, zero on the fill
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_kkt_scatter(LpView v, KktDev d, int64_t nnz) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    for (int64_t q = mp.first; q < nnz; q += mp.stride) d.W[(int64_t)d.kmap[q] * B + mp.s] = v.A[q * B + mp.s];
+}
+
+// =================================== barrier iteration ==========================================================
+struct ColFlags {
+    bool fx, hl, hu;
+};
+__device__ __forceinline__ ColFlags col_flags(double l, double u) {
+    ColFlags f;
+    f.fx = (l == u);
+    f.hl = ipm_fin(l) && !f.fx;
+    f.hu = ipm_fin(u) && !f.fx;
+    return f;
+}
+struct RowFlags {
+    bool eq, gl, gu;
+};
+__device__ __forceinline__ RowFlags row_flags(double l, double u) {
+    RowFlags f;
+    f.eq = (l == u);
+    f.gl = ipm_fin(l) && !f.eq;
+    f.gu = ipm_fin(u) && !f.eq;
+    return f;
+}
+
+// starting point: x inside its box (0 where the box allows), w = Kx pushed inside the row bounds, z = 1, y = 0
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_init_cols(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    double acc[3] = {0.0, 0.0, 0.0};  // complementarity pairs, inconsistent boxes, |x|^2 unscaled
+    const double inv_sb = 1.0 / v.state[mp.s].sb;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        const double l = v.lbs[e], u = v.ubs[e];
+        const ColFlags f = col_flags(l, u);
+        double x0 = 0.0;
+        if (f.fx)
+            x0 = l;
+        else if (f.hl && f.hu)
+            x0 = fmin(fmax(0.0, l + 0.1 * (u - l)), u - 0.1 * (u - l));
+        else if (f.hl)
+            x0 = fmax(0.0, l + 1.0);
+        else if (f.hu)
+            x0 = fmin(0.0, u - 1.0);
+        g.x[e] = x0;
+        g.zlx[e] = f.hl ? 1.0 : 0.0;
+        g.zux[e] = f.hu ? 1.0 : 0.0;
+        acc[0] += (f.hl ? 1.0 : 0.0) + (f.hu ? 1.0 : 0.0);
+        if (l > u) acc[1] += 1.0;
+        const double xu = x0 * v.dc[e] * inv_sb;
+        acc[2] += xu * xu;
+    }
+    block_reduce_store<BATCH, 3>(acc, 0u, v.partials, 0, B);
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_init_rows(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    double acc[2] = {0.0, 0.0};
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        const double l = v.rls[e], u = v.rus[e];
+        const RowFlags f = row_flags(l, u);
+        const double ax = spmv_row(v.A, v.col_idx, g.x, v.row_ptr[i], v.row_ptr[i + 1], B, mp.s);
+        double w0 = ax;
+        if (f.eq)
+            w0 = l;
+        else if (f.gl && f.gu)
+            w0 = fmin(fmax(ax, l + 0.1 * (u - l)), u - 0.1 * (u - l));
+        else if (f.gl)
+            w0 = fmax(ax, l + 1.0);
+        else if (f.gu)
+            w0 = fmin(ax, u - 1.0);
+        g.w[e] = w0;
+        g.y[e] = 0.0;
+        g.zlw[e] = f.gl ? 1.0 : 0.0;
+        g.zuw[e] = f.gu ? 1.0 : 0.0;
+        acc[0] += (f.gl ? 1.0 : 0.0) + (f.gu ? 1.0 : 0.0);
+        if (l > u) acc[1] += 1.0;
+    }
+    block_reduce_store<BATCH, 2>(acc, 0u, v.partials, 3, B);
+}
+__global__ void __launch_bounds__(kFinalThreads) k_ipm_init_state(LpView v, IpmView g) {
+    const int s = blockIdx.x, B = v.B;
+    const double nc = final_reduce(v.partials, 0, v.nbx_cols, B, s, false);
+    const double badc = final_reduce(v.partials, 1, v.nbx_cols, B, s, false);
+    const double xn2 = final_reduce(v.partials, 2, v.nbx_cols, B, s, false);
+    const double nr = final_reduce(v.partials, 3, v.nbx_rows, B, s, false);
+    const double badr = final_reduce(v.partials, 4, v.nbx_rows, B, s, false);
+    if (threadIdx.x) return;
+    ScenState *st = v.state + s;
+    IpmState it;
+    it.mu = 1.0;
+    it.smu = 0.0;
+    it.ap = it.ad = 0.0;
+    it.q_un = 0.5 * g.prox * (1.0 + st->nc_un) / fmax(1.0, sqrt(xn2));
+    it.qs = it.q_un * st->sc / st->sb;
+    it.ncomp = (int)(nc + nr + 0.5);
+    it.hits = 0;
+    it.save = 0;
+    it.bad = (badc + badr) > 0.0;
+    g.ist[s] = it;
+    if (st->status < 0 && it.bad) {  // lb > ub or rl > ru: nothing to iterate on
+        st->status = ASM_LP_INFEASIBLE;
+        st->total = 0;
+        atomicSub(v.n_active, 1);
+    }
+}
+
+// residuals of the barrier system and everything the termination / Farkas tests need
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_res_cols(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const ScenState *st = v.state + mp.s;
+    const bool live = st->status < 0;
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+        const double inv_sc = 1.0 / st->sc, inv_sb = 1.0 / st->sb, qs = g.ist[mp.s].qs;
+        for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+            const int64_t e = j * B + mp.s;
+            const double l = v.lbs[e], u = v.ubs[e], c = v.cs[e], x = g.x[e], d = v.dc[e];
+            const ColFlags f = col_flags(l, u);
+            const double aty = spmv_row(v.AT, v.row_idx, g.y, v.col_ptr[j], v.col_ptr[j + 1], B, mp.s);
+            const double Q = f.fx ? 0.0 : qs * d * d;
+            const double zl = g.zlx[e], zu = g.zux[e];
+            const double rlp = c - aty - zl + zu;
+            const double r = rlp + Q * x;
+            g.rdx[e] = r;
+            if (!f.fx) {
+                const double ru = r * inv_sc / d, rl2 = rlp * inv_sc / d;
+                acc[I_RDX2] += ru * ru;
+                acc[I_RLP2] += rl2 * rl2;
+            }
+            acc[I_POBJ] += c * x;
+            acc[I_QT] += 0.5 * Q * x * x;
+            acc[I_DOBJC] += (f.hl ? l * zl : 0.0) - (f.hu ? u * zu : 0.0) + (f.fx ? l * (c - aty) : 0.0);
+            acc[I_MUC] += (f.hl ? zl * (x - l) : 0.0) + (f.hu ? zu * (u - x) : 0.0);
+            const double xu = x * d * inv_sb;
+            acc[I_XN2] += xu * xu;
+            const double t = -aty;
+            acc[I_RAYC] += t > 0.0 ? t * l : (t < 0.0 ? t * u : 0.0);
+            acc[I_KTY] = fmax(acc[I_KTY], fabs(aty / d));
+        }
+    }
+    block_reduce_store<BATCH, 9>(acc, 1u << I_KTY, v.partials, 0, B);
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_res_rows(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const ScenState *st = v.state + mp.s;
+    const bool live = st->status < 0;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    if (live) {
+        const double inv_sc = 1.0 / st->sc, inv_sb = 1.0 / st->sb;
+        for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+            const int64_t e = i * B + mp.s;
+            const double l = v.rls[e], u = v.rus[e], d = v.dr[e], y = g.y[e];
+            const RowFlags f = row_flags(l, u);
+            const double ax = spmv_row(v.A, v.col_idx, g.x, v.row_ptr[i], v.row_ptr[i + 1], B, mp.s);
+            const double w = f.eq ? l : g.w[e];
+            const double zl = g.zlw[e], zu = g.zuw[e];
+            const double rp = ax - w;
+            const double rd = f.eq ? 0.0 : y - zl + zu;
+            g.rp[e] = rp;
+            g.rdw[e] = rd;
+            const double rpu = rp * inv_sb / d, rdu = rd * d * inv_sc;
+            acc[0] += rpu * rpu;
+            acc[1] += rdu * rdu;
+            acc[2] += f.eq ? l * y : ((f.gl ? l * zl : 0.0) - (f.gu ? u * zu : 0.0));
+            acc[3] += (f.gl ? zl * (w - l) : 0.0) + (f.gu ? zu * (u - w) : 0.0);
+            acc[4] += y > 0.0 ? l * y : (y < 0.0 ? u * y : 0.0);
+            acc[5] = fmax(acc[5], fabs(y * d));
+        }
+    }
+    block_reduce_store<BATCH, 6>(acc, 1u << 5, v.partials, I_RP2, B);
+}
+
+// one block per LP: termination, Farkas test, proximal weight of the next step
+__global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView g, int iter, int last) {
+    const int s = blockIdx.x, B = v.B;
+    ScenState *sp = v.state + s;
+    if (sp->status >= 0) return;
+    double q[I_COUNT];
+    for (int i = 0; i < I_COUNT; ++i)
+        q[i] = final_reduce(v.partials, i, i >= I_RP2 ? v.nbx_rows : v.nbx_cols, B, s, i == I_KTY || i == I_YMAX);
+    if (threadIdx.x) return;
+    ScenState st = *sp;
+    IpmState it = g.ist[s];
+    const double unit = 1.0 / (st.sb * st.sc);
+    const double pq = (q[I_POBJ] + q[I_QT]) * unit, dq = (q[I_DOBJC] + q[I_DOBJR] - q[I_QT]) * unit;
+    const double pres = sqrt(q[I_RP2]), dres = sqrt(q[I_RDX2] + q[I_RDW2]);
+    const double gapq = fabs(pq - dq);
+    it.mu = it.ncomp > 0 ? (q[I_MUC] + q[I_MUR]) / it.ncomp : 0.0;
+    // what is reported is measured against the LP itself (no proximal term)
+    st.pobj = q[I_POBJ] * unit;
+    st.dobj = (q[I_DOBJC] + q[I_DOBJR]) * unit;
+    st.pres = pres;
+    st.dres = sqrt(q[I_RLP2] + q[I_RDW2]);
+    st.gap = fabs(st.pobj - st.dobj);
+    st.total = iter;
+    const bool conv = pres <= g.eps * (1.0 + st.nq_un) && dres <= g.eps * (1.0 + st.nc_un) &&
+                      gapq <= g.eps * (1.0 + fabs(pq) + fabs(dq));
+    const bool nan = !(pres == pres) || !(dres == dres) || !(gapq == gapq) || !(it.mu == it.mu);
+    int status = -1;
+    it.save = 0;
+    if (conv && !nan) {
+        it.hits += 1;
+        it.save = 1;
+        if (it.hits > g.extra_hits || it.mu <= 1e-30) status = ASM_LP_OPTIMAL;
+    } else if (it.hits > 0) {
+        status = ASM_LP_OPTIMAL;  // the point saved at the previous step stands
+    } else if (nan) {
+        status = ASM_LP_NUMERICAL_ERROR;
+    } else {
+        const double nr = q[I_YMAX] / st.sc;
+        if (nr > 0.0 && iter > 0) {
+            const double robj = (q[I_RAYR] + q[I_RAYC]) * unit / nr;
+            const double kty = q[I_KTY] / st.sc / nr;
+            if (robj > v.prm->eps_infeas * fmax(1.0, kty)) status = ASM_LP_INFEASIBLE;
+        }
+    }
+    if (status < 0 && last) {
+        status = ASM_LP_ITERATION_LIMIT;
+        it.save = 1;
+    }
+    if (g.verbose && s == 0)
+        printf("[ipm] it %3d pres %.3e dres %.3e gap %.3e mu %.3e pobj %.12e q %.3e ap %.3f ad %.3f%s\n", iter, pres,
+               dres, gapq, it.mu, st.pobj, it.q_un, it.ap, it.ad, status >= 0 ? " *" : "");
+    it.q_un = 0.5 * g.prox * (1.0 + st.nc_un) / fmax(1.0, sqrt(q[I_XN2]));
+    it.qs = it.q_un * st.sc / st.sb;
+    g.ist[s] = it;
+    if (status >= 0) {
+        st.status = status;
+        atomicSub(v.n_active, 1);
+    }
+    *sp = st;
+}
+
+// keep the current point as the result (xp, yp, reduced costs in gyp -- what k_finalize reads); variables that sit
+// strictly complementary on a bound go exactly onto it
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_save(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    if (!g.ist[mp.s].save) return;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        const double l = v.lbs[e], u = v.ubs[e];
+        const ColFlags f = col_flags(l, u);
+        double x = g.x[e];
+        const double zl = g.zlx[e], zu = g.zux[e];
+        if (f.fx) {
+            x = l;
+        } else {
+            const double span = (f.hl && f.hu) ? u - l : 1.0;
+            if (f.hl && x - l < zl && x - l <= 1e-5 * fmax(span, fabs(l))) x = l;
+            if (f.hu && u - x < zu && u - x <= 1e-5 * fmax(span, fabs(u))) x = u;
+        }
+        v.xp[e] = x;
+        v.gyp[e] = f.fx ? g.rdx[e] : zl - zu;
+    }
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        v.yp[e] = g.y[e];
+    }
+}
+
+// diagonal blocks of the Newton system
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_diag(LpView v, IpmView g, KktDev d) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    if (v.state[mp.s].status >= 0) return;
+    const double qs = g.ist[mp.s].qs;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        const double l = v.lbs[e], u = v.ubs[e], x = g.x[e], dc = v.dc[e];
+        const ColFlags f = col_flags(l, u);
+        double D = (f.hl ? g.zlx[e] / (x - l) : 0.0) + (f.hu ? g.zux[e] / (u - x) : 0.0) + qs * dc * dc;
+        if (f.fx) D = 1e20;
+        g.Dx[e] = D;
+        d.diag0[(int64_t)d.inv[j] * B + mp.s] = -(D + g.delta);
+        d.invd[(int64_t)d.inv[j] * B + mp.s] = -1.0 / (D + g.delta);
+    }
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        const double l = v.rls[e], u = v.rus[e], w = g.w[e];
+        const RowFlags f = row_flags(l, u);
+        const double D = (f.gl ? g.zlw[e] / (w - l) : 0.0) + (f.gu ? g.zuw[e] / (u - w) : 0.0);
+        const double E = f.eq ? 0.0 : fmin(1.0 / fmax(D, 1e-300), 1e20);
+        g.Ew[e] = E;
+        d.diag0[(int64_t)d.inv[v.n + i] * B + mp.s] = E + g.delta;
+        d.invd[(int64_t)d.inv[v.n + i] * B + mp.s] = 1.0 / (E + g.delta);
+    }
+}
+
+// right-hand side of the reduced system; CORR adds the centring target sigma*mu and the second-order products
+template <bool BATCH, bool CORR>
+__global__ void __launch_bounds__(kThreads) k_ipm_rhs(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    if (v.state[mp.s].status >= 0) return;
+    const double smu = CORR ? g.ist[mp.s].smu : 0.0;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        const double l = v.lbs[e], u = v.ubs[e], x = g.x[e];
+        const ColFlags f = col_flags(l, u);
+        const double tl = f.hl ? (smu - (CORR ? g.clx[e] : 0.0)) / (x - l) - g.zlx[e] : 0.0;
+        const double tu = f.hu ? (smu - (CORR ? g.cux[e] : 0.0)) / (u - x) - g.zux[e] : 0.0;
+        const double r = f.fx ? 0.0 : -(-g.rdx[e] + tl - tu);
+        g.rhs0[e] = r;
+        g.sol[e] = r;
+    }
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        const double l = v.rls[e], u = v.rus[e], w = g.w[e];
+        const RowFlags f = row_flags(l, u);
+        const double tl = f.gl ? (smu - (CORR ? g.clw[e] : 0.0)) / (w - l) - g.zlw[e] : 0.0;
+        const double tu = f.gu ? (smu - (CORR ? g.cuw[e] : 0.0)) / (u - w) - g.zuw[e] : 0.0;
+        const double rw = -g.rdw[e] + tl - tu;
+        const double r = -g.rp[e] + (f.eq ? 0.0 : g.Ew[e] * rw);
+        const int64_t en = ((int64_t)v.n + i) * B + mp.s;
+        g.rhs0[en] = r;
+        g.sol[en] = r;
+    }
+}
+
+// iterative refinement: work = rhs0 - M0 sol with the unregularised blocks
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_kkt_res_cols(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    if (v.state[mp.s].status >= 0) return;
+    const double *s2 = g.sol + (int64_t)v.n * B;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        const double a = spmv_row(v.AT, v.row_idx, s2, v.col_ptr[j], v.col_ptr[j + 1], B, mp.s);
+        g.work[e] = g.rhs0[e] - (a - g.Dx[e] * g.sol[e]);
+    }
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_kkt_res_rows(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    if (v.state[mp.s].status >= 0) return;
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t en = ((int64_t)v.n + i) * B + mp.s;
+        const double a = spmv_row(v.A, v.col_idx, g.sol, v.row_ptr[i], v.row_ptr[i + 1], B, mp.s);
+        g.work[en] = g.rhs0[en] - (a + g.Ew[i * B + mp.s] * g.sol[en]);
+    }
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_kkt_add(LpView v, IpmView g, int64_t N) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    if (v.state[mp.s].status >= 0) return;
+    for (int64_t i = mp.first; i < N; i += mp.stride) g.sol[i * B + mp.s] += g.work[i * B + mp.s];
+}
+
+// directions of the eliminated variables and the ratio tests (as max of -d/s, no division by a small slack)
+template <bool BATCH, bool CORR>
+__global__ void __launch_bounds__(kThreads) k_ipm_dirs_cols(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const bool live = v.state[mp.s].status < 0;
+    double acc[2] = {0.0, 0.0};
+    if (live) {
+        const double smu = CORR ? g.ist[mp.s].smu : 0.0;
+        for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+            const int64_t e = j * B + mp.s;
+            const double l = v.lbs[e], u = v.ubs[e], x = g.x[e];
+            const ColFlags f = col_flags(l, u);
+            if (f.fx) g.sol[e] = 0.0;
+            const double dx = f.fx ? 0.0 : g.sol[e];
+            double dl = 0.0, du = 0.0;
+            if (f.hl) {
+                const double sl = x - l, z = g.zlx[e];
+                dl = (smu - (CORR ? g.clx[e] : 0.0)) / sl - z - z / sl * dx;
+                acc[0] = fmax(acc[0], -dx / sl);
+                acc[1] = fmax(acc[1], -dl / z);
+            }
+            if (f.hu) {
+                const double su = u - x, z = g.zux[e];
+                du = (smu - (CORR ? g.cux[e] : 0.0)) / su - z + z / su * dx;
+                acc[0] = fmax(acc[0], dx / su);
+                acc[1] = fmax(acc[1], -du / z);
+            }
+            g.dzlx[e] = dl;
+            g.dzux[e] = du;
+        }
+    }
+    block_reduce_store<BATCH, 2>(acc, 3u, v.partials, J_AP, B);
+}
+template <bool BATCH, bool CORR>
+__global__ void __launch_bounds__(kThreads) k_ipm_dirs_rows(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const bool live = v.state[mp.s].status < 0;
+    double acc[2] = {0.0, 0.0};
+    if (live) {
+        const double smu = CORR ? g.ist[mp.s].smu : 0.0;
+        for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+            const int64_t e = i * B + mp.s;
+            const double l = v.rls[e], u = v.rus[e], w = g.w[e];
+            const RowFlags f = row_flags(l, u);
+            const double dy = g.sol[((int64_t)v.n + i) * B + mp.s];
+            const double tl = f.gl ? (smu - (CORR ? g.clw[e] : 0.0)) / (w - l) - g.zlw[e] : 0.0;
+            const double tu = f.gu ? (smu - (CORR ? g.cuw[e] : 0.0)) / (u - w) - g.zuw[e] : 0.0;
+            const double dw = f.eq ? 0.0 : g.Ew[e] * (-g.rdw[e] + tl - tu - dy);
+            double dl = 0.0, du = 0.0;
+            if (f.gl) {
+                const double sl = w - l, z = g.zlw[e];
+                dl = tl - z / sl * dw;
+                acc[0] = fmax(acc[0], -dw / sl);
+                acc[1] = fmax(acc[1], -dl / z);
+            }
+            if (f.gu) {
+                const double su = u - w, z = g.zuw[e];
+                du = tu + z / su * dw;
+                acc[0] = fmax(acc[0], dw / su);
+                acc[1] = fmax(acc[1], -du / z);
+            }
+            g.dw[e] = dw;
+            g.dzlw[e] = dl;
+            g.dzuw[e] = du;
+        }
+    }
+    block_reduce_store<BATCH, 2>(acc, 3u, v.partials, J_AP_R, B);
+}
+// complementarity after the affine step and the second-order products of the corrector
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_muaff(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const bool live = v.state[mp.s].status < 0;
+    double acc[2] = {0.0, 0.0};  // columns, rows
+    if (live) {
+        const double ap = g.ist[mp.s].ap, ad = g.ist[mp.s].ad;
+        for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+            const int64_t e = j * B + mp.s;
+            const double l = v.lbs[e], u = v.ubs[e], x = g.x[e];
+            const ColFlags f = col_flags(l, u);
+            const double dx = g.sol[e];
+            if (f.hl) {
+                acc[0] += (x - l + ap * dx) * (g.zlx[e] + ad * g.dzlx[e]);
+                g.clx[e] = dx * g.dzlx[e];
+            }
+            if (f.hu) {
+                acc[0] += (u - x - ap * dx) * (g.zux[e] + ad * g.dzux[e]);
+                g.cux[e] = -dx * g.dzux[e];
+            }
+        }
+        for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+            const int64_t e = i * B + mp.s;
+            const double l = v.rls[e], u = v.rus[e], w = g.w[e];
+            const RowFlags f = row_flags(l, u);
+            const double dw = g.dw[e];
+            if (f.gl) {
+                acc[1] += (w - l + ap * dw) * (g.zlw[e] + ad * g.dzlw[e]);
+                g.clw[e] = dw * g.dzlw[e];
+            }
+            if (f.gu) {
+                acc[1] += (u - w - ap * dw) * (g.zuw[e] + ad * g.dzuw[e]);
+                g.cuw[e] = -dw * g.dzuw[e];
+            }
+        }
+    }
+    block_reduce_store<BATCH, 2>(acc, 0u, v.partials, J_MUC, B);
+}
+// one block per LP.  mode 0: affine step lengths; 1: sigma from the affine complementarity; 2: damped final lengths
+__global__ void __launch_bounds__(kFinalThreads) k_ipm_scalars(LpView v, IpmView g, int mode, int nbx_both) {
+    const int s = blockIdx.x, B = v.B;
+    if (v.state[s].status >= 0) return;
+    if (mode == 1) {
+        const double mc = final_reduce(v.partials, J_MUC, nbx_both, B, s, false);
+        const double mr = final_reduce(v.partials, J_MUR, nbx_both, B, s, false);
+        if (threadIdx.x) return;
+        IpmState it = g.ist[s];
+        const double mu_aff = it.ncomp > 0 ? (mc + mr) / it.ncomp : 0.0;
+        double sg = it.mu > 0.0 ? mu_aff / it.mu : 0.0;
+        sg = fmin(fmax(sg, 0.0), 1.0);
+        it.smu = sg * sg * sg * it.mu;
+        g.ist[s] = it;
+        return;
+    }
+    const double pc = final_reduce(v.partials, J_AP, v.nbx_cols, B, s, true);
+    const double dc = final_reduce(v.partials, J_AD, v.nbx_cols, B, s, true);
+    const double pr = final_reduce(v.partials, J_AP_R, v.nbx_rows, B, s, true);
+    const double dr = final_reduce(v.partials, J_AD_R, v.nbx_rows, B, s, true);
+    if (threadIdx.x) return;
+    const double damp = mode == 2 ? 0.995 : 1.0;
+    const double ip = fmax(pc, pr), id = fmax(dc, dr);
+    IpmState it = g.ist[s];
+    it.ap = ip > damp ? damp / ip : 1.0;
+    it.ad = id > damp ? damp / id : 1.0;
+    g.ist[s] = it;
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_update(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    if (v.state[mp.s].status >= 0) return;
+    const double ap = g.ist[mp.s].ap, ad = g.ist[mp.s].ad;
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+        const int64_t e = j * B + mp.s;
+        g.x[e] += ap * g.sol[e];
+        g.zlx[e] += ad * g.dzlx[e];
+        g.zux[e] += ad * g.dzux[e];
+    }
+    for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+        const int64_t e = i * B + mp.s;
+        g.w[e] += ap * g.dw[e];
+        g.y[e] += ad * g.sol[((int64_t)v.n + i) * B + mp.s];
+        g.zlw[e] += ad * g.dzlw[e];
+        g.zuw[e] += ad * g.dzuw[e];
+    }
+}
+
+// =================================== host side ================================================================
+struct IpmEngine {
+    KktSymbolic sym;
+    bool ready = false;
+    int B = 0;
+    DBuf<int> fchunk, fstep, wchunk, wstep, bstep, perm, inv, kmap;
+    DBuf<KktTerm> terms;
+    DBuf<KktFwdItem> fwd;
+    DBuf<KktBwdItem> bwd;
+    DBuf<double> W, invd, diag0;
+    DBuf<double> colv[9], rowv[12], kktv[3];
+    DBuf<IpmState> ist;
+    cudaGraphExec_t g_factor = nullptr, g_solve_sol = nullptr, g_solve_work = nullptr;
+    int64_t launches_factor = 0, launches_solve = 0;
+    double symbolic_ms = 0.0;
+    int last_newton = 0;
+    float last_factor_ms = 0.f, last_solve_ms = 0.f;
+
+    ~IpmEngine() {
+        if (g_factor) cudaGraphExecDestroy(g_factor);
+        if (g_solve_sol) cudaGraphExecDestroy(g_solve_sol);
+        if (g_solve_work) cudaGraphExecDestroy(g_solve_work);
+    }
+
+    template <class T>
+    static int up(DBuf<T> &dst, const std::vector<T> &src) {
+        ASM_TRY(dst.alloc(std::max<size_t>(src.size(), 1)));
+        if (!src.empty()) ASM_CK(cudaMemcpy(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return ASM_OK;
+    }
+
+    int init(int n, int m, const std::vector<int> &row_ptr, const std::vector<int> &col_idx, int B_) {
+        B = B_;
+        for (int i = 0; i < m; ++i) {   // the assembly writes one value per entry of L: no duplicate (row, column) pairs
+            std::vector<int> cols(col_idx.begin() + row_ptr[i], col_idx.begin() + row_ptr[i + 1]);
+            std::sort(cols.begin(), cols.end());
+            if (std::adjacent_find(cols.begin(), cols.end()) != cols.end())
+                return fail(ASM_E_INVALID, "duplicate (row, column) entries in the pattern: the barrier engine needs a deduplicated CSR");
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        if (sym.build(n, m, row_ptr.data(), col_idx.data(), B == 1 ? 2048 : 64))
+            return fail(ASM_E_INVALID, "KKT symbolic analysis failed (index out of range or more than 2^31 update terms)");
+        symbolic_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        ASM_TRY(up(terms, sym.terms));
+        ASM_TRY(up(fchunk, sym.fchunk));
+        ASM_TRY(up(fstep, sym.fstep));
+        ASM_TRY(up(fwd, sym.fwd));
+        ASM_TRY(up(wchunk, sym.wchunk));
+        ASM_TRY(up(wstep, sym.wstep));
+        ASM_TRY(up(bwd, sym.bwd));
+        ASM_TRY(up(bstep, sym.bstep));
+        ASM_TRY(up(perm, sym.perm));
+        ASM_TRY(up(inv, sym.inv));
+        ASM_TRY(up(kmap, sym.kmap));
+        // the big host lists are not needed any more
+        std::vector<KktTerm>().swap(sym.terms);
+        std::vector<KktFwdItem>().swap(sym.fwd);
+        std::vector<KktBwdItem>().swap(sym.bwd);
+        std::vector<int>().swap(sym.fchunk);
+        const size_t N = sym.N;
+        ASM_TRY(W.alloc(std::max<size_t>(sym.nnzL, 1) * B));
+        ASM_TRY(invd.alloc(N * B));
+        ASM_TRY(diag0.alloc(N * B));
+        for (auto &b : colv) ASM_TRY(b.alloc((size_t)n * B));
+        for (auto &b : rowv) ASM_TRY(b.alloc((size_t)std::max(m, 1) * B));
+        for (auto &b : kktv) ASM_TRY(b.alloc(N * B));
+        ASM_TRY(ist.alloc(B));
+        ready = true;
+        return ASM_OK;
+    }
+
+    KktDev dev() const {
+        KktDev d;
+        d.terms = terms.p;
+        d.fchunk = fchunk.p;
+        d.fstep = fstep.p;
+        d.fwd = fwd.p;
+        d.wchunk = wchunk.p;
+        d.wstep = wstep.p;
+        d.bwd = bwd.p;
+        d.bstep = bstep.p;
+        d.perm = perm.p;
+        d.inv = inv.p;
+        d.kmap = kmap.p;
+        d.W = W.p;
+        d.invd = invd.p;
+        d.diag0 = diag0.p;
+        d.nnzL = (int)sym.nnzL;
+        d.N = sym.N;
+        return d;
+    }
+    IpmView iview(const asm_lp_params &P) {
+        IpmView g;
+        double **c[] = {&g.x, &g.zlx, &g.zux, &g.rdx, &g.Dx, &g.dzlx, &g.dzux, &g.clx, &g.cux};
+        for (int i = 0; i < 9; ++i) *c[i] = colv[i].p;
+        double **r[] = {&g.w, &g.y, &g.zlw, &g.zuw, &g.rp, &g.rdw, &g.Ew, &g.dw, &g.dzlw, &g.dzuw, &g.clw, &g.cuw};
+        for (int i = 0; i < 12; ++i) *r[i] = rowv[i].p;
+        g.rhs0 = kktv[0].p;
+        g.sol = kktv[1].p;
+        g.work = kktv[2].p;
+        g.ist = ist.p;
+        g.delta = P.ipm_reg > 0.0 ? P.ipm_reg : 1e-8;
+        g.prox = P.ipm_prox >= 0.0 ? P.ipm_prox : 1e-6;
+        g.eps = std::min(P.eps_rel, 1e-8);
+        g.extra_hits = 2;
+        g.verbose = P.verbose;
+        return g;
+    }
+
+    // grid of a step kernel.  Batch: a warp per item, scenarios over blockIdx.y; single LP: a thread per item
+    dim3 level_grid(const KktLaunch &L) const {
+        unsigned gx = 1;
+        const int per_block = B == 1 ? kThreads : kWarps;
+        if (!L.fused) {
+            const int gy = B == 1 ? 1 : B / 32;
+            int64_t cap = std::max<int64_t>(1, (int64_t)kMaxBlocksX * 4 / gy);
+            gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L.items + per_block - 1) / per_block, cap));
+        }
+        return dim3(gx, B == 1 ? 1 : B / 32);
+    }
+    void enqueue_factor(LpView &v, cudaStream_t st, int64_t &count) {
+        KktDev d = dev();
+        cudaMemsetAsync(W.p, 0, W.n * sizeof(double), st);
+        const int64_t nz = (int64_t)sym.kmap.size();
+        if (nz) {
+            const Geo gz = geo_for(nz, B);
+            if (B > 1)
+                k_kkt_scatter<true><<<gz.grid, gz.block, 0, st>>>(v, d, nz);
+            else
+                k_kkt_scatter<false><<<gz.grid, gz.block, 0, st>>>(v, d, nz);
+        }
+        count += 2;
+        for (const KktLaunch &L : sym.flaunch) {
+            const dim3 grid = level_grid(L);
+            if (B > 1) {
+                if (L.fused)
+                    k_ldl_factor<true, true><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state);
+                else
+                    k_ldl_factor<true, false><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state);
+            } else {
+                if (L.fused)
+                    k_ldl_factor<false, true><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state);
+                else
+                    k_ldl_factor<false, false><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state);
+            }
+            ++count;
+        }
+    }
+    void enqueue_solve(LpView &v, double *vec, cudaStream_t st, int64_t &count) {
+        KktDev d = dev();
+        for (const KktLaunch &L : sym.wlaunch) {
+            const dim3 grid = level_grid(L);
+            if (B > 1) {
+                if (L.fused)
+                    k_ldl_fwd<true, true><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                else
+                    k_ldl_fwd<true, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+            } else {
+                if (L.fused)
+                    k_ldl_fwd<false, true><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                else
+                    k_ldl_fwd<false, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+            }
+            ++count;
+        }
+        {
+            const Geo gN = geo_for(sym.N, B);
+            if (B > 1)
+                k_ldl_diag<true><<<gN.grid, gN.block, 0, st>>>(d, vec, B, v.state);
+            else
+                k_ldl_diag<false><<<gN.grid, gN.block, 0, st>>>(d, vec, B, v.state);
+            ++count;
+        }
+        for (auto it = sym.blaunch.rbegin(); it != sym.blaunch.rend(); ++it) {
+            const KktLaunch &L = *it;
+            const dim3 grid = level_grid(L);
+            if (B > 1) {
+                if (L.fused)
+                    k_ldl_bwd<true, true><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                else
+                    k_ldl_bwd<true, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+            } else {
+                if (L.fused)
+                    k_ldl_bwd<false, true><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                else
+                    k_ldl_bwd<false, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+            }
+            ++count;
+        }
+    }
+    // the level sequences never change for a handle: captured once, replayed every Newton step
+    template <class F>
+    int capture(cudaStream_t st, cudaGraphExec_t *exec, int64_t &count, F body) {
+        if (*exec) return ASM_OK;
+        cudaGraph_t graph = nullptr;
+        count = 0;
+        ASM_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        body(count);
+        ASM_CK(cudaStreamEndCapture(st, &graph));
+        ASM_CK(cudaGraphInstantiate(exec, graph, 0));
+        ASM_CK(cudaGraphDestroy(graph));
+        return ASM_OK;
+    }
+};
+
+}  // namespace asmb

@@ -64,6 +64,7 @@ enum {
     Q_KTY_MAX,   // max |(A'ray)_j / dc_j|
     Q_COUNT
 };
+constexpr int kPartialSlots = 16;  // rows of the partial buffer: Q_COUNT here, I_COUNT in ipm.cuh
 // preparation slots (reuse the same partial buffer)
 enum { P_C2 = 0, P_CUN2, P_Q2, P_QUN2, P_COUNT };
 
@@ -730,6 +731,7 @@ __global__ void __launch_bounds__(kThreads) k_finalize(LpView v) {
 
 }  // namespace asmb
 #include "pdhg_group.cuh"
+#include "ipm.cuh"
 namespace asmb {
 
 // ---- live-set compaction of a streaming batch ------------------------------------------------------------------
@@ -814,6 +816,8 @@ class LpSolver {
     int homeB = 0, homeBuser = 0;
     int compactions = 0;
     int last_engine = 0, last_G = 0, last_groups = 0;
+    std::unique_ptr<IpmEngine> ipm;   // barrier engine (ipm.cuh), built at the first solve that uses it
+    int ipm_failed = 0;               // symbolic analysis refused this pattern: engine 0 stays on PDHG
     // data (unscaled, element-major)
     DBuf<double> vals, c, lb, ub, rl, ru, c0;
     DBuf<double> A, AT, dr, dc, sr, scf, cs, lbs, ubs, rls, rus;
@@ -905,7 +909,7 @@ class LpSolver {
         ASM_TRY(A.alloc(zB));
         ASM_TRY(AT.alloc(zB));
         ASM_TRY(c0.alloc(B));
-        ASM_TRY(partials.alloc((size_t)Q_COUNT * kMaxBlocksX * B));
+        ASM_TRY(partials.alloc((size_t)kPartialSlots * kMaxBlocksX * B));
         ASM_TRY(gmax.alloc(B));
         ASM_TRY(state.alloc(B));
         ASM_TRY(prm.alloc(1));
@@ -1507,6 +1511,96 @@ class LpSolver {
         return ASM_OK;
     }
 
+    // ---- barrier engine: Mehrotra predictor-corrector on the fixed-pattern L D L' (ipm.cuh) ----------------------
+    int ensure_ipm() {
+        if (ipm) return ASM_OK;
+        std::unique_ptr<IpmEngine> e(new IpmEngine);
+        const int rc = e->init(n, m, h_row_ptr, h_col_idx, B);
+        if (rc != ASM_OK) {
+            ipm_failed = 1;
+            return rc;
+        }
+        ipm = std::move(e);
+        return ASM_OK;
+    }
+    int solve_ipm(const asm_lp_params &P, int *flag) {
+        ASM_TRY(ensure_ipm());
+        IpmEngine &E = *ipm;
+        LpView v = view();
+        IpmView g = E.iview(P);
+        KktDev d = E.dev();
+        const Geo gr = geo_for(m, B), gc = geo_for(n, B), gm = geo_for(std::max(n, m), B), gN = geo_for((int64_t)n + m, B);
+        const int refine = P.ipm_refine >= 0 ? P.ipm_refine : 2;
+        const int max_it = P.ipm_max_iter > 0 ? P.ipm_max_iter : 200;
+        const bool trace = getenv("ASM_TRACE") != nullptr;
+        ASM_TRY(E.capture(stream, &E.g_factor, E.launches_factor, [&](int64_t &c) { E.enqueue_factor(v, stream, c); }));
+        ASM_TRY(E.capture(stream, &E.g_solve_sol, E.launches_solve, [&](int64_t &c) { E.enqueue_solve(v, g.sol, stream, c); }));
+        ASM_TRY(E.capture(stream, &E.g_solve_work, E.launches_solve, [&](int64_t &c) { E.enqueue_solve(v, g.work, stream, c); }));
+        auto solve_refined = [&]() -> int {
+            ASM_CK(cudaGraphLaunch(E.g_solve_sol, stream));
+            launches += E.launches_solve;
+            for (int r = 0; r < refine; ++r) {
+                ASM_KB(k_kkt_res_cols, gc, v, g);
+                ASM_KB(k_kkt_res_rows, gr, v, g);
+                ASM_CK(cudaGraphLaunch(E.g_solve_work, stream));
+                launches += E.launches_solve;
+                ASM_KB(k_kkt_add, gN, v, g, (int64_t)n + m);
+            }
+            return ASM_OK;
+        };
+        ASM_KB(k_ipm_init_cols, gc, v, g);
+        ASM_KB(k_ipm_init_rows, gr, v, g);
+        ASM_KL(k_ipm_init_state<<<B, kFinalThreads, 0, stream>>>(v, g));
+        int it = 0;
+        for (;; ++it) {
+            ASM_KB(k_ipm_res_cols, gc, v, g);
+            ASM_KB(k_ipm_res_rows, gr, v, g);
+            ASM_KL(k_ipm_decide<<<B, kFinalThreads, 0, stream>>>(v, g, it, it >= max_it ? 1 : 0));
+            ASM_KB(k_ipm_save, gm, v, g);
+            ASM_CK(cudaMemcpyAsync(flag, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            ASM_CK(cudaStreamSynchronize(stream));
+            if (*flag <= 0 || it >= max_it) break;
+            ASM_KB(k_ipm_diag, gm, v, g, d);
+            const bool timed = trace && it == 1;
+            cudaEvent_t te[3] = {nullptr, nullptr, nullptr};
+            if (timed) {
+                for (auto &e : te) cudaEventCreate(&e);
+                cudaEventRecord(te[0], stream);
+            }
+            ASM_CK(cudaGraphLaunch(E.g_factor, stream));
+            launches += E.launches_factor;
+            if (timed) cudaEventRecord(te[1], stream);
+            ASM_KB2(k_ipm_rhs, false, gm, v, g);
+            ASM_TRY(solve_refined());
+            if (timed) {
+                cudaEventRecord(te[2], stream);
+                cudaEventSynchronize(te[2]);
+                cudaEventElapsedTime(&E.last_factor_ms, te[0], te[1]);
+                cudaEventElapsedTime(&E.last_solve_ms, te[1], te[2]);
+                fprintf(stderr, "[asm] barrier engine: N %d nnz(L) %lld terms %lld levels %d | factor %.3f ms (%lld launches) | "
+                        "solve + %d refinements %.3f ms (%lld launches per substitution pair) | symbolic %.0f ms\n",
+                        E.sym.N, (long long)E.sym.nnzL, (long long)E.sym.nterms, E.sym.n_levels, E.last_factor_ms,
+                        (long long)E.launches_factor, refine, E.last_solve_ms, (long long)E.launches_solve, E.symbolic_ms);
+                for (auto &e : te) cudaEventDestroy(e);
+            }
+            ASM_KB2(k_ipm_dirs_cols, false, gc, v, g);
+            ASM_KB2(k_ipm_dirs_rows, false, gr, v, g);
+            ASM_KL(k_ipm_scalars<<<B, kFinalThreads, 0, stream>>>(v, g, 0, (int)gm.grid.x));
+            ASM_KB(k_ipm_muaff, gm, v, g);
+            ASM_KL(k_ipm_scalars<<<B, kFinalThreads, 0, stream>>>(v, g, 1, (int)gm.grid.x));
+            ASM_KB2(k_ipm_rhs, true, gm, v, g);
+            ASM_TRY(solve_refined());
+            ASM_KB2(k_ipm_dirs_cols, true, gc, v, g);
+            ASM_KB2(k_ipm_dirs_rows, true, gr, v, g);
+            ASM_KL(k_ipm_scalars<<<B, kFinalThreads, 0, stream>>>(v, g, 2, (int)gm.grid.x));
+            ASM_KB(k_ipm_update, gm, v, g);
+            ASM_CK(cudaGetLastError());
+        }
+        E.last_newton = it;
+        last_engine = 4;
+        return ASM_OK;
+    }
+
     // average device time of one launch of each streaming kernel; scenarios are re-activated for the measurement
     int time_streaming_kernels(int reps, double *primal_ms, double *dual_ms) {
         LpView v = view();
@@ -1592,7 +1686,13 @@ class LpSolver {
         ASM_CK(cudaMemcpyAsync(prm.p, pdp, sizeof dp, cudaMemcpyHostToDevice, stream));
         ASM_CK(cudaMemcpyAsync(n_active.p, flag, sizeof(int), cudaMemcpyHostToDevice, stream));
         tiny_rel = P.tiny_rel > 0.0 ? P.tiny_rel : kTinyRel;
-        ASM_TRY(precondition(P.ruiz_iters, (P.warm_start && has_solution) ? (int)P.warm_start : 0));
+        // engine 0 (auto) and 4: barrier method on the fixed-pattern L D L'; 1 / 2 / 5: the PDHG engines
+        bool use_ipm = P.engine == 4 || (P.engine == 0 && !ipm_failed);
+        if (use_ipm && ensure_ipm() != ASM_OK) {
+            if (P.engine == 4) return ASM_E_INVALID;
+            use_ipm = false;
+        }
+        ASM_TRY(precondition(P.ruiz_iters, (!use_ipm && P.warm_start && has_solution) ? (int)P.warm_start : 0));
         const int steps = std::max(2, (int)P.check_every);
         // engine 1: streaming kernels only (one launch per half iteration, CUDA graph per check period);
         // engine 2: persistent group kernel only;
@@ -1603,7 +1703,8 @@ class LpSolver {
         homeBuser = Buser;
         compactions = 0;
         const int hand_over = Buser == 1 ? 0 : std::max(1, std::min(Buser, (int)(P.hand_over * Buser)));
-        const bool plan_ok = P.engine != 1 && ensure_plan(P.group_size, P.engine == 2 ? Buser : std::max(1, hand_over)) == ASM_OK;
+        const bool plan_ok = !use_ipm && P.engine != 1 &&
+                             ensure_plan(P.group_size, P.engine == 2 ? Buser : std::max(1, hand_over)) == ASM_OK;
         if (P.engine == 2 && !plan_ok) return ensure_plan(P.group_size, Buser);
         const bool group_only = plan_ok && (P.engine == 2 || Buser == 1);
         ASM_CK(cudaEventRecord(ev0, stream));
@@ -1615,7 +1716,10 @@ class LpSolver {
         const bool trace = getenv("ASM_TRACE") != nullptr;
         auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         double t_phase = now();
-        if (!group_only) {
+        if (use_ipm) {
+            ASM_TRY(solve_ipm(P, flag));
+            live = 0;
+        } else if (!group_only) {
             // cost model (seconds per iteration of one running LP), calibrated on B200 (profiles/): the streaming
             // kernels move the whole working set at ~4.4 TB/s plus two launches; the group kernel costs
             // (sync + work / G) on G of the machine's SMs
@@ -1640,7 +1744,7 @@ class LpSolver {
                 ASM_CK(cudaStreamSynchronize(stream));
                 live = *flag;
                 if (live <= 0) break;
-                const bool shrink = P.engine == 0 && B >= 128 && pad_batch(live) * 2 <= B;
+                const bool shrink = (P.engine == 0 || P.engine == 5) && B >= 128 && pad_batch(live) * 2 <= B;
                 if (plan_ok && live <= hand_over && group_cost(live) < stream_cost(shrink ? pad_batch(live) : B, live)) break;
                 if (shrink) {
                     LpView vv = view();
@@ -1658,7 +1762,7 @@ class LpSolver {
             last_engine |= 1;
         }
         // group phase: re-planned as the live set thins out (wider groups for the last stragglers)
-        if (trace && !group_only)
+        if (trace && !group_only && !use_ipm)
             fprintf(stderr, "[asm] streaming phase done: %d LPs still running (%.3f s since last event)\n", live, now() - t_phase);
         t_phase = now();
         while (plan_ok && live > 0 && !limit) {

@@ -64,8 +64,11 @@ typedef struct asm_lp_params {
     double restart_necessary;  /* 0.8  */
     double restart_artificial; /* 0.36 */
     double pid_kp, pid_ki, pid_kd; /* primal-weight controller on log(w |dx|/|dy|); (0.5, 0, 0) = PDLP rule  */
-    int32_t engine;        /* 0 auto; 1 streaming kernels (one launch per half iteration, CUDA graph);       */
-                           /* 2 persistent group kernel (LP resident in the shared memory of G blocks)       */
+    int32_t engine;        /* 0 auto (the barrier engine; PDHG hybrid if the pattern is refused);            */
+                           /* 1 PDHG streaming kernels (one launch per half iteration, CUDA graph);          */
+                           /* 2 PDHG persistent group kernel (LP resident in the shared memory of G blocks)  */
+                           /* 4 barrier method: Mehrotra predictor-corrector on a fixed-pattern L D L'       */
+                           /* 5 PDHG hybrid: stream, compact, hand the stragglers to the group kernel        */
     int32_t group_size;    /* blocks per LP for engine 2 (0 = auto)                                          */
     double hand_over;      /* engine 0 on a batch: fraction of the batch still running at which the          */
                            /* streaming kernels hand the stragglers to the group kernel (default 0.5)        */
@@ -73,6 +76,12 @@ typedef struct asm_lp_params {
                            /* residual)^weight_balance instead of the PDLP rule (0 = PDLP rule, the default)          */
     double tiny_rel;       /* rows / columns whose largest coefficient is below tiny_rel * max|K| are treated as     */
                            /* empty by the equilibration (0 = default 1e-8)                                            */
+    /* barrier engine (engine 0 / 4) */
+    int32_t ipm_max_iter;  /* Newton steps per LP (default 200)                                                        */
+    int32_t ipm_refine;    /* iterative-refinement passes per linear solve (default 2)                                 */
+    double ipm_reg;        /* static regularisation d of the quasi-definite system (default 1e-8, scaled units)        */
+    double ipm_prox;       /* least-norm selection: proximal weight q = ipm_prox (1 + |c|) / (2 max(1, |x|)), i.e. the */
+                           /* relative dual residual it may leave in the LP (default 1e-6; 0 = pure LP)                */
 } asm_lp_params;
 void asm_lp_default_params(asm_lp_params *p);
 
