@@ -44,11 +44,12 @@ enum {
     I_COUNT
 };
 // slots reused inside a Newton step (the residual slots are consumed by k_ipm_decide before)
-enum { J_AP = 0, J_AD, J_MUC, J_MUR, J_AP_R, J_AD_R };
+enum { J_AP = 0, J_AD, J_MUC, J_MUR, J_AP_R, J_AD_R, J_RAY /* 4 slots */ };
 
 struct IpmState {
     double mu, smu, ap, ad, qs, q_un;
-    int ncomp, hits, save, bad;
+    double ray_obj, ray_kty;  // Farkas test of the last step direction dy (normalised)
+    int ncomp, hits, acc_hits, save, bad;
 };
 
 struct KktDev {
@@ -71,11 +72,15 @@ struct IpmView {
     // KKT vectors (node order: columns then rows)
     double *rhs0, *sol, *work;
     IpmState *ist;
-    double delta, prox, eps;
+    const double *c0;     // objective constants (the termination test is relative to the objective the caller sees)
+    double delta, prox;
+    double eps, eps_acc;  // target tolerance; acceptable tolerance (kept as a fall-back result when the target is not reached)
     int extra_hits, verbose;
 };
 
 __device__ __forceinline__ bool ipm_fin(double v) { return fabs(v) < 1.79e308; }
+// distance to a bound; below the resolution of the difference it is floored (the complementarity products stay finite)
+__device__ __forceinline__ double ipm_slack(double d) { return fmax(d, 1e-30); }
 
 // =================================== numeric L D L' ============================================================
 // Step l applies the updates of the columns of level l to their targets (fan-out).  A chunk = the terms of one target
@@ -201,7 +206,7 @@ __device__ __forceinline__ RowFlags row_flags(double l, double u) {
     return f;
 }
 
-// starting point: x inside its box (0 where the box allows), w = Kx pushed inside the row bounds, z = 1, y = 0
+// starting point: x inside its box (0 where the box allows), w = Kx pushed inside the row bounds, z = 1 / slack, y = 0
 template <bool BATCH>
 __global__ void __launch_bounds__(kThreads) k_ipm_init_cols(LpView v, IpmView g) {
     Map<BATCH> mp;
@@ -222,8 +227,10 @@ __global__ void __launch_bounds__(kThreads) k_ipm_init_cols(LpView v, IpmView g)
         else if (f.hu)
             x0 = fmin(0.0, u - 1.0);
         g.x[e] = x0;
-        g.zlx[e] = f.hl ? 1.0 : 0.0;
-        g.zux[e] = f.hu ? 1.0 : 0.0;
+        // centred start: every complementarity product is 1, whatever the width of the box (a collapsed trust region
+        // gives boxes of 1e-6 next to row slacks of order one)
+        g.zlx[e] = f.hl ? 1.0 / (x0 - l) : 0.0;
+        g.zux[e] = f.hu ? 1.0 / (u - x0) : 0.0;
         acc[0] += (f.hl ? 1.0 : 0.0) + (f.hu ? 1.0 : 0.0);
         if (l > u) acc[1] += 1.0;
         const double xu = x0 * v.dc[e] * inv_sb;
@@ -252,8 +259,8 @@ __global__ void __launch_bounds__(kThreads) k_ipm_init_rows(LpView v, IpmView g)
             w0 = fmin(ax, u - 1.0);
         g.w[e] = w0;
         g.y[e] = 0.0;
-        g.zlw[e] = f.gl ? 1.0 : 0.0;
-        g.zuw[e] = f.gu ? 1.0 : 0.0;
+        g.zlw[e] = f.gl ? 1.0 / (w0 - l) : 0.0;
+        g.zuw[e] = f.gu ? 1.0 / (u - w0) : 0.0;
         acc[0] += (f.gl ? 1.0 : 0.0) + (f.gu ? 1.0 : 0.0);
         if (l > u) acc[1] += 1.0;
     }
@@ -276,7 +283,10 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_init_state(LpView v, IpmV
     it.qs = it.q_un * st->sc / st->sb;
     it.ncomp = (int)(nc + nr + 0.5);
     it.hits = 0;
+    it.acc_hits = 0;
     it.save = 0;
+    it.ray_obj = -1.0;
+    it.ray_kty = 1.0;
     it.bad = (badc + badr) > 0.0;
     g.ist[s] = it;
     if (st->status < 0 && it.bad) {  // lb > ub or rl > ru: nothing to iterate on
@@ -379,34 +389,47 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
     st.dres = sqrt(q[I_RLP2] + q[I_RDW2]);
     st.gap = fabs(st.pobj - st.dobj);
     st.total = iter;
-    const bool conv = pres <= g.eps * (1.0 + st.nq_un) && dres <= g.eps * (1.0 + st.nc_un) &&
-                      gapq <= g.eps * (1.0 + fabs(pq) + fabs(dq));
+    const double c0 = g.c0[s];
+    const double gden = 1.0 + fabs(pq + c0) + fabs(dq + c0);
+    auto within = [&](double e) {
+        return pres <= e * (1.0 + st.nq_un) && dres <= e * (1.0 + st.nc_un) && gapq <= e * gden;
+    };
     const bool nan = !(pres == pres) || !(dres == dres) || !(gapq == gapq) || !(it.mu == it.mu);
+    const bool conv = !nan && within(g.eps), acc = !nan && within(g.eps_acc);
     int status = -1;
     it.save = 0;
-    if (conv && !nan) {
+    if (conv) {
+        // a few more steps sharpen the least-norm selection, unless the complementarity is already at the resolution
+        // of the slacks
         it.hits += 1;
         it.save = 1;
-        if (it.hits > g.extra_hits || it.mu <= 1e-30) status = ASM_LP_OPTIMAL;
+        if (it.hits > g.extra_hits || it.mu <= 1e-14) status = ASM_LP_OPTIMAL;
     } else if (it.hits > 0) {
         status = ASM_LP_OPTIMAL;  // the point saved at the previous step stands
+    } else if (acc) {
+        it.acc_hits += 1;         // fall-back result should the target tolerance not be reached
+        it.save = 1;
     } else if (nan) {
-        status = ASM_LP_NUMERICAL_ERROR;
+        status = it.acc_hits > 0 ? ASM_LP_OPTIMAL : ASM_LP_NUMERICAL_ERROR;
     } else {
+        // Farkas certificate from y itself and from the last step direction dy (the one that grows when the LP is
+        // infeasible); both normalised to |ray|_inf = 1 in unscaled units
         const double nr = q[I_YMAX] / st.sc;
         if (nr > 0.0 && iter > 0) {
             const double robj = (q[I_RAYR] + q[I_RAYC]) * unit / nr;
             const double kty = q[I_KTY] / st.sc / nr;
             if (robj > v.prm->eps_infeas * fmax(1.0, kty)) status = ASM_LP_INFEASIBLE;
         }
+        if (status < 0 && it.acc_hits == 0 && it.ray_obj > v.prm->eps_infeas * fmax(1.0, it.ray_kty)) status = ASM_LP_INFEASIBLE;
     }
     if (status < 0 && last) {
-        status = ASM_LP_ITERATION_LIMIT;
-        it.save = 1;
+        status = it.acc_hits > 0 ? ASM_LP_OPTIMAL : ASM_LP_ITERATION_LIMIT;
+        if (it.acc_hits == 0) it.save = 1;
     }
     if (g.verbose && s == 0)
-        printf("[ipm] it %3d pres %.3e dres %.3e gap %.3e mu %.3e pobj %.12e q %.3e ap %.3f ad %.3f%s\n", iter, pres,
-               dres, gapq, it.mu, st.pobj, it.q_un, it.ap, it.ad, status >= 0 ? " *" : "");
+        printf("[ipm] it %3d pres %.3e dres %.3e gap %.3e mu %.3e pobj %.12e q %.3e ap %.3f ad %.3f ray %.2e%s%s\n", iter,
+               pres / (1.0 + st.nq_un), dres / (1.0 + st.nc_un), gapq / gden, it.mu, st.pobj + c0, it.q_un, it.ap, it.ad,
+               it.ray_obj, acc ? " a" : "", status >= 0 ? " *" : "");
     it.q_un = 0.5 * g.prox * (1.0 + st.nc_un) / fmax(1.0, sqrt(q[I_XN2]));
     it.qs = it.q_un * st.sc / st.sb;
     g.ist[s] = it;
@@ -457,7 +480,7 @@ __global__ void __launch_bounds__(kThreads) k_ipm_diag(LpView v, IpmView g, KktD
         const int64_t e = j * B + mp.s;
         const double l = v.lbs[e], u = v.ubs[e], x = g.x[e], dc = v.dc[e];
         const ColFlags f = col_flags(l, u);
-        double D = (f.hl ? g.zlx[e] / (x - l) : 0.0) + (f.hu ? g.zux[e] / (u - x) : 0.0) + qs * dc * dc;
+        double D = (f.hl ? g.zlx[e] / ipm_slack(x - l) : 0.0) + (f.hu ? g.zux[e] / ipm_slack(u - x) : 0.0) + qs * dc * dc;
         if (f.fx) D = 1e20;
         g.Dx[e] = D;
         d.diag0[(int64_t)d.inv[j] * B + mp.s] = -(D + g.delta);
@@ -467,7 +490,7 @@ __global__ void __launch_bounds__(kThreads) k_ipm_diag(LpView v, IpmView g, KktD
         const int64_t e = i * B + mp.s;
         const double l = v.rls[e], u = v.rus[e], w = g.w[e];
         const RowFlags f = row_flags(l, u);
-        const double D = (f.gl ? g.zlw[e] / (w - l) : 0.0) + (f.gu ? g.zuw[e] / (u - w) : 0.0);
+        const double D = (f.gl ? g.zlw[e] / ipm_slack(w - l) : 0.0) + (f.gu ? g.zuw[e] / ipm_slack(u - w) : 0.0);
         const double E = f.eq ? 0.0 : fmin(1.0 / fmax(D, 1e-300), 1e20);
         g.Ew[e] = E;
         d.diag0[(int64_t)d.inv[v.n + i] * B + mp.s] = E + g.delta;
@@ -486,8 +509,8 @@ __global__ void __launch_bounds__(kThreads) k_ipm_rhs(LpView v, IpmView g) {
         const int64_t e = j * B + mp.s;
         const double l = v.lbs[e], u = v.ubs[e], x = g.x[e];
         const ColFlags f = col_flags(l, u);
-        const double tl = f.hl ? (smu - (CORR ? g.clx[e] : 0.0)) / (x - l) - g.zlx[e] : 0.0;
-        const double tu = f.hu ? (smu - (CORR ? g.cux[e] : 0.0)) / (u - x) - g.zux[e] : 0.0;
+        const double tl = f.hl ? (smu - (CORR ? g.clx[e] : 0.0)) / ipm_slack(x - l) - g.zlx[e] : 0.0;
+        const double tu = f.hu ? (smu - (CORR ? g.cux[e] : 0.0)) / ipm_slack(u - x) - g.zux[e] : 0.0;
         const double r = f.fx ? 0.0 : -(-g.rdx[e] + tl - tu);
         g.rhs0[e] = r;
         g.sol[e] = r;
@@ -496,8 +519,8 @@ __global__ void __launch_bounds__(kThreads) k_ipm_rhs(LpView v, IpmView g) {
         const int64_t e = i * B + mp.s;
         const double l = v.rls[e], u = v.rus[e], w = g.w[e];
         const RowFlags f = row_flags(l, u);
-        const double tl = f.gl ? (smu - (CORR ? g.clw[e] : 0.0)) / (w - l) - g.zlw[e] : 0.0;
-        const double tu = f.gu ? (smu - (CORR ? g.cuw[e] : 0.0)) / (u - w) - g.zuw[e] : 0.0;
+        const double tl = f.gl ? (smu - (CORR ? g.clw[e] : 0.0)) / ipm_slack(w - l) - g.zlw[e] : 0.0;
+        const double tu = f.gu ? (smu - (CORR ? g.cuw[e] : 0.0)) / ipm_slack(u - w) - g.zuw[e] : 0.0;
         const double rw = -g.rdw[e] + tl - tu;
         const double r = -g.rp[e] + (f.eq ? 0.0 : g.Ew[e] * rw);
         const int64_t en = ((int64_t)v.n + i) * B + mp.s;
@@ -555,13 +578,13 @@ __global__ void __launch_bounds__(kThreads) k_ipm_dirs_cols(LpView v, IpmView g)
             const double dx = f.fx ? 0.0 : g.sol[e];
             double dl = 0.0, du = 0.0;
             if (f.hl) {
-                const double sl = x - l, z = g.zlx[e];
+                const double sl = ipm_slack(x - l), z = fmax(g.zlx[e], 1e-300);
                 dl = (smu - (CORR ? g.clx[e] : 0.0)) / sl - z - z / sl * dx;
                 acc[0] = fmax(acc[0], -dx / sl);
                 acc[1] = fmax(acc[1], -dl / z);
             }
             if (f.hu) {
-                const double su = u - x, z = g.zux[e];
+                const double su = ipm_slack(u - x), z = fmax(g.zux[e], 1e-300);
                 du = (smu - (CORR ? g.cux[e] : 0.0)) / su - z + z / su * dx;
                 acc[0] = fmax(acc[0], dx / su);
                 acc[1] = fmax(acc[1], -du / z);
@@ -585,18 +608,18 @@ __global__ void __launch_bounds__(kThreads) k_ipm_dirs_rows(LpView v, IpmView g)
             const double l = v.rls[e], u = v.rus[e], w = g.w[e];
             const RowFlags f = row_flags(l, u);
             const double dy = g.sol[((int64_t)v.n + i) * B + mp.s];
-            const double tl = f.gl ? (smu - (CORR ? g.clw[e] : 0.0)) / (w - l) - g.zlw[e] : 0.0;
-            const double tu = f.gu ? (smu - (CORR ? g.cuw[e] : 0.0)) / (u - w) - g.zuw[e] : 0.0;
+            const double tl = f.gl ? (smu - (CORR ? g.clw[e] : 0.0)) / ipm_slack(w - l) - g.zlw[e] : 0.0;
+            const double tu = f.gu ? (smu - (CORR ? g.cuw[e] : 0.0)) / ipm_slack(u - w) - g.zuw[e] : 0.0;
             const double dw = f.eq ? 0.0 : g.Ew[e] * (-g.rdw[e] + tl - tu - dy);
             double dl = 0.0, du = 0.0;
             if (f.gl) {
-                const double sl = w - l, z = g.zlw[e];
+                const double sl = ipm_slack(w - l), z = fmax(g.zlw[e], 1e-300);
                 dl = tl - z / sl * dw;
                 acc[0] = fmax(acc[0], -dw / sl);
                 acc[1] = fmax(acc[1], -dl / z);
             }
             if (f.gu) {
-                const double su = u - w, z = g.zuw[e];
+                const double su = ipm_slack(u - w), z = fmax(g.zuw[e], 1e-300);
                 du = tu + z / su * dw;
                 acc[0] = fmax(acc[0], dw / su);
                 acc[1] = fmax(acc[1], -du / z);
@@ -648,6 +671,46 @@ __global__ void __launch_bounds__(kThreads) k_ipm_muaff(LpView v, IpmView g) {
     }
     block_reduce_store<BATCH, 2>(acc, 0u, v.partials, J_MUC, B);
 }
+// Farkas quantities of the step direction dy = sol[n:], projected on the sign cone of the one-sided rows
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_ray(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const bool live = v.state[mp.s].status < 0;
+    double acc[2] = {0.0, 0.0};  // row part, |ray|_inf
+    if (live) {
+        double *ray = g.work + (int64_t)v.n * B;   // the refinement buffer is free at this point
+        for (int64_t i = mp.first; i < v.m; i += mp.stride) {
+            const int64_t e = i * B + mp.s;
+            const double l = v.rls[e], u = v.rus[e];
+            double d = g.sol[((int64_t)v.n + i) * B + mp.s];
+            if (!ipm_fin(l)) d = fmin(d, 0.0);
+            if (!ipm_fin(u)) d = fmax(d, 0.0);
+            ray[e] = d;
+            acc[0] += d > 0.0 ? l * d : (d < 0.0 ? u * d : 0.0);
+            acc[1] = fmax(acc[1], fabs(d * v.dr[e]));
+        }
+    }
+    block_reduce_store<BATCH, 2>(acc, 2u, v.partials, J_RAY, B);
+}
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_ray_cols(LpView v, IpmView g) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    const bool live = v.state[mp.s].status < 0;
+    double acc[2] = {0.0, 0.0};  // column part (box support of -K'ray), |K'ray|_inf
+    if (live) {
+        const double *ray = g.work + (int64_t)v.n * B;
+        for (int64_t j = mp.first; j < v.n; j += mp.stride) {
+            const int64_t e = j * B + mp.s;
+            const double a = spmv_row(v.AT, v.row_idx, ray, v.col_ptr[j], v.col_ptr[j + 1], B, mp.s);
+            const double t = -a;
+            acc[0] += t > 0.0 ? t * v.lbs[e] : (t < 0.0 ? t * v.ubs[e] : 0.0);
+            acc[1] = fmax(acc[1], fabs(a / v.dc[e]));
+        }
+    }
+    block_reduce_store<BATCH, 2>(acc, 2u, v.partials, J_RAY + 2, B);
+}
 // one block per LP.  mode 0: affine step lengths; 1: sigma from the affine complementarity; 2: damped final lengths
 __global__ void __launch_bounds__(kFinalThreads) k_ipm_scalars(LpView v, IpmView g, int mode, int nbx_both) {
     const int s = blockIdx.x, B = v.B;
@@ -668,10 +731,23 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_scalars(LpView v, IpmView
     const double dc = final_reduce(v.partials, J_AD, v.nbx_cols, B, s, true);
     const double pr = final_reduce(v.partials, J_AP_R, v.nbx_rows, B, s, true);
     const double dr = final_reduce(v.partials, J_AD_R, v.nbx_rows, B, s, true);
+    double rr = 0.0, rm = 0.0, rc = 0.0, rk = 0.0;
+    if (mode == 2) {
+        rr = final_reduce(v.partials, J_RAY, v.nbx_rows, B, s, false);
+        rm = final_reduce(v.partials, J_RAY + 1, v.nbx_rows, B, s, true);
+        rc = final_reduce(v.partials, J_RAY + 2, v.nbx_cols, B, s, false);
+        rk = final_reduce(v.partials, J_RAY + 3, v.nbx_cols, B, s, true);
+    }
     if (threadIdx.x) return;
     const double damp = mode == 2 ? 0.995 : 1.0;
     const double ip = fmax(pc, pr), id = fmax(dc, dr);
     IpmState it = g.ist[s];
+    if (mode == 2) {
+        const ScenState *st = v.state + s;
+        const double nr = rm / st->sc;
+        it.ray_obj = nr > 0.0 ? (rr + rc) / (st->sb * st->sc) / nr : -1.0;
+        it.ray_kty = nr > 0.0 ? rk / st->sc / nr : 1.0;
+    }
     it.ap = ip > damp ? damp / ip : 1.0;
     it.ad = id > damp ? damp / id : 1.0;
     g.ist[s] = it;
@@ -801,6 +877,7 @@ struct IpmEngine {
         g.delta = P.ipm_reg > 0.0 ? P.ipm_reg : 1e-8;
         g.prox = P.ipm_prox >= 0.0 ? P.ipm_prox : 1e-6;
         g.eps = std::min(P.eps_rel, 1e-8);
+        g.eps_acc = std::max(P.eps_rel, 1e-7);
         g.extra_hits = 2;
         g.verbose = P.verbose;
         return g;

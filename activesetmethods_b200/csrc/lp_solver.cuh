@@ -1528,6 +1528,7 @@ class LpSolver {
         IpmEngine &E = *ipm;
         LpView v = view();
         IpmView g = E.iview(P);
+        g.c0 = c0.p;
         KktDev d = E.dev();
         const Geo gr = geo_for(m, B), gc = geo_for(n, B), gm = geo_for(std::max(n, m), B), gN = geo_for((int64_t)n + m, B);
         const int refine = P.ipm_refine >= 0 ? P.ipm_refine : 2;
@@ -1592,6 +1593,8 @@ class LpSolver {
             ASM_TRY(solve_refined());
             ASM_KB2(k_ipm_dirs_cols, true, gc, v, g);
             ASM_KB2(k_ipm_dirs_rows, true, gr, v, g);
+            ASM_KB(k_ipm_ray, gr, v, g);
+            ASM_KB(k_ipm_ray_cols, gc, v, g);
             ASM_KL(k_ipm_scalars<<<B, kFinalThreads, 0, stream>>>(v, g, 2, (int)gm.grid.x));
             ASM_KB(k_ipm_update, gm, v, g);
             ASM_CK(cudaGetLastError());
