@@ -932,7 +932,7 @@ void asm_lp_default_params(asm_lp_params *p) {
     p->ipm_max_iter = 200;
     p->ipm_refine = 2;
     p->ipm_reg = 1e-8;
-    p->ipm_prox = 1e-6;
+    p->ipm_prox = 1e-7;
 }
 
 // ---- generic LP -------------------------------------------------------------------------------------------------
@@ -1568,6 +1568,77 @@ int asm_slp_kernel_timing(asm_slp *h, int32_t reps, double *primal_ms, double *d
     if (!h->h.solved) return fail(ASM_E_STATE, "no solve yet");
     ASM_CK(cudaSetDevice(h->h.device));
     return h->h.cur()->time_streaming_kernels(reps, primal_ms, dual_ms);
+}
+
+// sizes of the barrier engine's factorisation (stats[8]: KKT dimension, nnz(L), update terms, levels, factor chunks,
+// forward chunks, launches per factorisation, launches per substitution pair) and (times[4]) symbolic analysis ms,
+// Newton steps of the last solve, factor / solve ms of the traced step (ASM_TRACE)
+int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times) {
+    if (!h) return fail(ASM_E_INVALID, "null handle");
+    LpSolver *lp = h->h.cur();
+    if (!lp || !lp->ipm) return fail(ASM_E_STATE, "the barrier engine has not run on this handle");
+    const IpmEngine &E = *lp->ipm;
+    if (stats) {
+        stats[0] = E.sym.N;
+        stats[1] = E.sym.nnzL;
+        stats[2] = E.sym.nterms;
+        stats[3] = E.sym.n_levels;
+        stats[4] = E.n_fchunks;
+        stats[5] = (int64_t)E.sym.wchunk.size() - 1;
+        stats[6] = E.launches_factor;
+        stats[7] = E.launches_solve;
+    }
+    if (times) {
+        times[0] = E.symbolic_ms;
+        times[1] = E.last_newton;
+        times[2] = E.last_factor_ms;
+        times[3] = E.last_solve_ms;
+    }
+    return ASM_OK;
+}
+int asm_slp_ipm_timing(asm_slp *h, int32_t reps, double *factor_ms, double *solve_ms) {
+    if (!h || reps < 1) return fail(ASM_E_INVALID, "bad argument");
+    if (!h->h.solved) return fail(ASM_E_STATE, "no solve yet");
+    ASM_CK(cudaSetDevice(h->h.device));
+    return h->h.cur()->time_ipm_kernels(reps, factor_ms, solve_ms);
+}
+
+// Host-only self test of the barrier engine's symbolic analysis (no device needed): orders and analyses the KKT
+// pattern of the m x n CSR matrix K, then factorises  [-diag(dx) K'; K diag(ew)]  and solves one right-hand side ON
+// THE HOST with exactly the lists and the summation order the device kernels use.  rhs_sol: n + m values, right-hand
+// side in (columns then rows), solution out.  stats[8]: nnz(L), terms, levels, factor launches, forward launches,
+// backward launches, longest chunk, chunks.
+int asm_kkt_selftest(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, const double *vals,
+                     const double *dx, const double *ew, double *rhs_sol, int64_t *stats) {
+    if (!row_ptr || n_cols <= 0 || n_rows < 0 || !dx || !rhs_sol) return fail(ASM_E_INVALID, "bad argument");
+    const int64_t nnz = row_ptr[n_rows];
+    if (nnz > 0 && (!col_idx || !vals)) return fail(ASM_E_INVALID, "null matrix");
+    std::vector<int> rp(n_rows + 1), ci(nnz);
+    for (int i = 0; i <= n_rows; ++i) rp[i] = (int)row_ptr[i];
+    for (int64_t k = 0; k < nnz; ++k) ci[k] = col_idx[k];
+    KktSymbolic S;
+    if (S.build(n_cols, n_rows, rp.data(), ci.data())) return fail(ASM_E_INVALID, "symbolic analysis failed");
+    std::vector<double> W(S.nnzL, 0.0), d0(S.N), invd;
+    for (int64_t q = 0; q < nnz; ++q) W[S.kmap[q]] = vals[q];
+    for (int j = 0; j < n_cols; ++j) d0[S.inv[j]] = -dx[j];
+    for (int i = 0; i < n_rows; ++i) d0[S.inv[n_cols + i]] = ew[i];
+    S.factor_host(W, d0, invd);
+    std::vector<double> v(rhs_sol, rhs_sol + S.N);
+    S.solve_host(W, invd, v);
+    std::copy(v.begin(), v.end(), rhs_sol);
+    if (stats) {
+        int64_t longest = 0;
+        for (size_t c = 0; c + 1 < S.fchunk.size(); ++c) longest = std::max<int64_t>(longest, S.fchunk[c + 1] - S.fchunk[c]);
+        stats[0] = S.nnzL;
+        stats[1] = S.nterms;
+        stats[2] = S.n_levels;
+        stats[3] = (int64_t)S.flaunch.size();
+        stats[4] = (int64_t)S.wlaunch.size();
+        stats[5] = (int64_t)S.blaunch.size();
+        stats[6] = longest;
+        stats[7] = (int64_t)S.fchunk.size() - 1;
+    }
+    return ASM_OK;
 }
 
 }  // extern "C"

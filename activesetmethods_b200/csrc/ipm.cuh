@@ -16,8 +16,9 @@
 //   * Mehrotra predictor-corrector with every scalar decision taken on the device per scenario (k_ipm_decide,
 //     k_ipm_scalars); the host enqueues a fixed kernel sequence per Newton step and reads one 4-byte counter.
 // A small proximal term (q/2)|x|^2 selects the least-norm optimal step among the minimisers (restoration LPs,
-// min sum of slacks, always have a face of them); q is sized so that the dual residual it leaves in the LP stays
-// below ipm_prox * (1 + |c|).  Variables that end strictly complementary on a bound are returned exactly on it, as a
+// min sum of slacks, always have a face of them); q is sized so that the dual residual and the duality gap it leaves
+// in the LP stay below ipm_prox relative (for q below a threshold the minimiser is an exact LP solution anyway:
+// Mangasarian & Meyer 1979).  Variables that end strictly complementary on a bound are returned exactly on it, as a
 // simplex code does: the reference compares them with == (subproblem.jl:522-529).
 // Algorithm: textbook (Mehrotra 1992; Vanderbei's quasi-definite systems) -- nothing here comes from the reference.
 #pragma once
@@ -49,6 +50,7 @@ enum { J_AP = 0, J_AD, J_MUC, J_MUR, J_AP_R, J_AD_R, J_RAY /* 4 slots */ };
 struct IpmState {
     double mu, smu, ap, ad, qs, q_un;
     double ray_obj, ray_kty;  // Farkas test of the last step direction dy (normalised)
+    double kept[5];           // pobj, dobj, pres, dres, gap of the point kept by k_ipm_save
     int ncomp, hits, acc_hits, save, bad;
 };
 
@@ -75,6 +77,7 @@ struct IpmView {
     const double *c0;     // objective constants (the termination test is relative to the objective the caller sees)
     double delta, prox;
     double eps, eps_acc;  // target tolerance; acceptable tolerance (kept as a fall-back result when the target is not reached)
+    double mu_target;     // complementarity (scaled units) at which a converged LP stops
     int extra_hits, verbose;
 };
 
@@ -279,7 +282,10 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_init_state(LpView v, IpmV
     it.mu = 1.0;
     it.smu = 0.0;
     it.ap = it.ad = 0.0;
-    it.q_un = 0.5 * g.prox * (1.0 + st->nc_un) / fmax(1.0, sqrt(xn2));
+    {
+        const double xn = fmax(1.0, sqrt(xn2));
+        it.q_un = g.prox * fmin(0.5 * (1.0 + st->nc_un) / xn, 1.0 / (xn * xn));
+    }
     it.qs = it.q_un * st->sc / st->sb;
     it.ncomp = (int)(nc + nr + 0.5);
     it.hits = 0;
@@ -399,11 +405,13 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
     int status = -1;
     it.save = 0;
     if (conv) {
-        // a few more steps sharpen the least-norm selection, unless the complementarity is already at the resolution
-        // of the slacks
+        // a few more steps drive the complementarity down until the variables on a bound reach it to machine precision
+        // (what a vertex solver returns, and what the reference's == tests on bounds expect, subproblem.jl:522-529)
+        // and sharpen the least-norm selection
         it.hits += 1;
         it.save = 1;
-        if (it.hits > g.extra_hits || it.mu <= 1e-14) status = ASM_LP_OPTIMAL;
+        if ((it.hits > g.extra_hits && it.mu <= g.mu_target) || it.hits > g.extra_hits + 4 || it.mu <= 1e-26)
+            status = ASM_LP_OPTIMAL;
     } else if (it.hits > 0) {
         status = ASM_LP_OPTIMAL;  // the point saved at the previous step stands
     } else if (acc) {
@@ -426,12 +434,30 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
         status = it.acc_hits > 0 ? ASM_LP_OPTIMAL : ASM_LP_ITERATION_LIMIT;
         if (it.acc_hits == 0) it.save = 1;
     }
+    if (it.save) {
+        it.kept[0] = st.pobj;
+        it.kept[1] = st.dobj;
+        it.kept[2] = st.pres;
+        it.kept[3] = st.dres;
+        it.kept[4] = st.gap;
+    } else if (status == ASM_LP_OPTIMAL) {  // the result is the point kept earlier: report its numbers
+        st.pobj = it.kept[0];
+        st.dobj = it.kept[1];
+        st.pres = it.kept[2];
+        st.dres = it.kept[3];
+        st.gap = it.kept[4];
+    }
     if (g.verbose && s == 0)
         printf("[ipm] it %3d pres %.3e dres %.3e gap %.3e mu %.3e pobj %.12e q %.3e ap %.3f ad %.3f ray %.2e%s%s\n", iter,
                pres / (1.0 + st.nq_un), dres / (1.0 + st.nc_un), gapq / gden, it.mu, st.pobj + c0, it.q_un, it.ap, it.ad,
                it.ray_obj, acc ? " a" : "", status >= 0 ? " *" : "");
-    it.q_un = 0.5 * g.prox * (1.0 + st.nc_un) / fmax(1.0, sqrt(q[I_XN2]));
-    it.qs = it.q_un * st.sc / st.sb;
+    // proximal weight of the next step: the dual residual q |x| it leaves in the LP stays below prox (1 + |c|) / 2 and
+    // the duality gap q |x|^2 below prox (1 + 2 |c'x|)
+    {
+        const double xn = fmax(1.0, sqrt(q[I_XN2]));
+        it.q_un = g.prox * fmin(0.5 * (1.0 + st.nc_un) / xn, (1.0 + 2.0 * fabs(st.pobj)) / (xn * xn));
+        it.qs = it.q_un * st.sc / st.sb;
+    }
     g.ist[s] = it;
     if (status >= 0) {
         st.status = status;
@@ -457,8 +483,10 @@ __global__ void __launch_bounds__(kThreads) k_ipm_save(LpView v, IpmView g) {
             x = l;
         } else {
             const double span = (f.hl && f.hu) ? u - l : 1.0;
-            if (f.hl && x - l < zl && x - l <= 1e-5 * fmax(span, fabs(l))) x = l;
-            if (f.hu && u - x < zu && u - x <= 1e-5 * fmax(span, fabs(u))) x = u;
+            // strictly complementary and closer than 1e-9 relative: moving it onto the bound changes no row by more
+            // than the feasibility tolerance
+            if (f.hl && x - l < zl && x - l <= 1e-9 * fmax(span, fabs(l))) x = l;
+            if (f.hu && u - x < zu && u - x <= 1e-9 * fmax(span, fabs(u))) x = u;
         }
         v.xp[e] = x;
         v.gyp[e] = f.fx ? g.rdx[e] : zl - zu;
@@ -466,6 +494,27 @@ __global__ void __launch_bounds__(kThreads) k_ipm_save(LpView v, IpmView g) {
     for (int64_t i = mp.first; i < v.m; i += mp.stride) {
         const int64_t e = i * B + mp.s;
         v.yp[e] = g.y[e];
+    }
+}
+
+// objective of the returned (snapped) point, so that the reported number is the one of the point the caller receives
+template <bool BATCH>
+__global__ void __launch_bounds__(kThreads) k_ipm_final_obj(LpView v) {
+    Map<BATCH> mp;
+    const int B = v.B;
+    double acc[1] = {0.0};
+    for (int64_t j = mp.first; j < v.n; j += mp.stride) acc[0] += v.cs[j * B + mp.s] * v.xp[j * B + mp.s];
+    block_reduce_store<BATCH, 1>(acc, 0u, v.partials, 0, B);
+}
+__global__ void __launch_bounds__(kFinalThreads) k_ipm_final_state(LpView v, int Buser) {
+    const int s = blockIdx.x, B = v.B;
+    const double q = final_reduce(v.partials, 0, v.nbx_cols, B, s, false);
+    if (threadIdx.x || s >= Buser) return;
+    ScenState *st = v.state + s;
+    if (st->status == ASM_LP_OPTIMAL || st->status == ASM_LP_ITERATION_LIMIT) {
+        const double pobj = q / (st->sb * st->sc);
+        st->gap = fabs(pobj - st->dobj);
+        st->pobj = pobj;
     }
 }
 
@@ -789,6 +838,7 @@ struct IpmEngine {
     int64_t launches_factor = 0, launches_solve = 0;
     double symbolic_ms = 0.0;
     int last_newton = 0;
+    int64_t n_fchunks = 0;
     float last_factor_ms = 0.f, last_solve_ms = 0.f;
 
     ~IpmEngine() {
@@ -831,6 +881,7 @@ struct IpmEngine {
         std::vector<KktTerm>().swap(sym.terms);
         std::vector<KktFwdItem>().swap(sym.fwd);
         std::vector<KktBwdItem>().swap(sym.bwd);
+        n_fchunks = (int64_t)sym.fchunk.size() - 1;
         std::vector<int>().swap(sym.fchunk);
         const size_t N = sym.N;
         ASM_TRY(W.alloc(std::max<size_t>(sym.nnzL, 1) * B));
@@ -875,10 +926,11 @@ struct IpmEngine {
         g.work = kktv[2].p;
         g.ist = ist.p;
         g.delta = P.ipm_reg > 0.0 ? P.ipm_reg : 1e-8;
-        g.prox = P.ipm_prox >= 0.0 ? P.ipm_prox : 1e-6;
+        g.prox = P.ipm_prox >= 0.0 ? P.ipm_prox : 1e-7;
         g.eps = std::min(P.eps_rel, 1e-8);
         g.eps_acc = std::max(P.eps_rel, 1e-7);
         g.extra_hits = 2;
+        g.mu_target = 1e-19;
         g.verbose = P.verbose;
         return g;
     }

@@ -1599,8 +1599,44 @@ class LpSolver {
             ASM_KB(k_ipm_update, gm, v, g);
             ASM_CK(cudaGetLastError());
         }
+        ASM_KB(k_ipm_final_obj, gc, v);
+        ASM_KL(k_ipm_final_state<<<B, kFinalThreads, 0, stream>>>(v, Buser));
         E.last_newton = it;
         last_engine = 4;
+        return ASM_OK;
+    }
+
+    // average device time of one numeric factorisation and of one substitution pair of the barrier engine (CUDA events
+    // on this handle's stream); scenarios are re-activated for the measurement, the result buffers are not touched
+    int time_ipm_kernels(int reps, double *factor_ms, double *solve_ms) {
+        if (!ipm || !ipm->g_factor || !ipm->g_solve_work) return fail(ASM_E_STATE, "the barrier engine has not run on this handle");
+        IpmEngine &E = *ipm;
+        std::vector<ScenState> keep(B), live(B);
+        ASM_CK(cudaMemcpyAsync(keep.data(), state.p, sizeof(ScenState) * B, cudaMemcpyDeviceToHost, stream));
+        ASM_CK(cudaStreamSynchronize(stream));
+        live = keep;
+        for (int s = 0; s < Buser; ++s) live[s].status = -1;
+        ASM_CK(cudaMemcpyAsync(state.p, live.data(), sizeof(ScenState) * B, cudaMemcpyHostToDevice, stream));
+        float t = 0.f;
+        for (int w = 0; w < 2; ++w) {
+            ASM_CK(cudaGraphLaunch(E.g_factor, stream));
+            ASM_CK(cudaGraphLaunch(E.g_solve_work, stream));
+        }
+        ASM_CK(cudaEventRecord(ev0, stream));
+        for (int r = 0; r < reps; ++r) ASM_CK(cudaGraphLaunch(E.g_factor, stream));
+        ASM_CK(cudaEventRecord(ev1, stream));
+        ASM_CK(cudaEventSynchronize(ev1));
+        ASM_CK(cudaEventElapsedTime(&t, ev0, ev1));
+        if (factor_ms) *factor_ms = t / reps;
+        ASM_CK(cudaEventRecord(ev0, stream));
+        for (int r = 0; r < reps; ++r) ASM_CK(cudaGraphLaunch(E.g_solve_work, stream));
+        ASM_CK(cudaEventRecord(ev1, stream));
+        ASM_CK(cudaEventSynchronize(ev1));
+        ASM_CK(cudaEventElapsedTime(&t, ev0, ev1));
+        if (solve_ms) *solve_ms = t / reps;
+        launches += (int64_t)(reps + 2) * (E.launches_factor + E.launches_solve);
+        ASM_CK(cudaMemcpyAsync(state.p, keep.data(), sizeof(ScenState) * B, cudaMemcpyHostToDevice, stream));
+        ASM_CK(cudaStreamSynchronize(stream));
         return ASM_OK;
     }
 

@@ -224,6 +224,24 @@ class SubLp:
         capi.check(self._lib.asm_slp_kernel_timing(self._h, int(reps), C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def ipm_info(self):
+        """Sizes of the barrier engine's factorisation and the Newton steps of the last solve."""
+        st = np.zeros(8, dtype=np.int64)
+        tm = np.zeros(4)
+        capi.check(self._lib.asm_slp_ipm_info(self._h, st.ctypes.data_as(capi.c_int64_p), capi.dptr(tm)))
+        keys = ("kkt_dim", "nnz_L", "terms", "levels", "factor_chunks", "forward_chunks", "launches_factor",
+                "launches_substitution")
+        out = {k: int(v) for k, v in zip(keys, st)}
+        out.update(symbolic_ms=float(tm[0]), newton_steps=int(tm[1]))
+        return out
+
+    def ipm_timing(self, reps=20):
+        """(factor_ms, substitution_pair_ms): device time per launch sequence of the whole batch, CUDA events."""
+        f = C.c_double()
+        s = C.c_double()
+        capi.check(self._lib.asm_slp_ipm_timing(self._h, int(reps), C.byref(f), C.byref(s)))
+        return f.value, s.value
+
     def engine_info(self):
         e = C.c_int32()
         g = C.c_int32()

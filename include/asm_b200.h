@@ -81,7 +81,7 @@ typedef struct asm_lp_params {
     int32_t ipm_refine;    /* iterative-refinement passes per linear solve (default 2)                                 */
     double ipm_reg;        /* static regularisation d of the quasi-definite system (default 1e-8, scaled units)        */
     double ipm_prox;       /* least-norm selection: proximal weight q = ipm_prox (1 + |c|) / (2 max(1, |x|)), i.e. the */
-                           /* relative dual residual it may leave in the LP (default 1e-6; 0 = pure LP)                */
+                           /* relative dual residual it may leave in the LP (default 1e-7; 0 = pure LP)                */
 } asm_lp_params;
 void asm_lp_default_params(asm_lp_params *p);
 
@@ -243,7 +243,21 @@ int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations);
  * whether the matrix values stay resident there, and the padded entry count of the row side */
 int asm_plan_check(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, int32_t G,
                    int64_t *smem_bytes, int32_t *matrix_resident, int64_t *padded_entries);
-/* which engine the last asm_slp_solve used (1 streaming, 2 group), blocks per LP and LPs resident at once */
+/* barrier engine (engine 0 / 4) instrumentation.  stats[8]: KKT dimension, nnz(L), update terms, levels, factor chunks,
+ * forward-substitution chunks, kernel launches per factorisation, per substitution pair; times[4]: symbolic analysis
+ * ms, Newton steps of the last solve, factor / solve ms of the traced step (ASM_TRACE=1).  Either pointer may be NULL */
+int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times);
+/* average device time (CUDA events on the handle's stream) of one numeric factorisation and one substitution pair of
+ * the whole batch, `reps` launches each, on the data of the last solve */
+int asm_slp_ipm_timing(asm_slp *h, int32_t reps, double *factor_ms, double *solve_ms);
+/* host-only self test of the barrier engine's symbolic analysis (no device needed): factorises
+ * [-diag(dx) K'; K diag(ew)] and solves one right-hand side on the host with the lists and the summation order of the
+ * device kernels.  rhs_sol[n_cols + n_rows]: right-hand side in, solution out.  stats[8]: nnz(L), terms, levels,
+ * factor / forward / backward launches, longest chunk, chunks */
+int asm_kkt_selftest(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, const double *vals,
+                     const double *dx, const double *ew, double *rhs_sol, int64_t *stats);
+
+/* which engine the last asm_slp_solve used (1 streaming, 2 group, 3 both, 4 barrier), blocks per LP and LPs resident at once */
 int asm_slp_engine_info(asm_slp *h, int32_t *engine, int32_t *group_size, int32_t *groups);
 
 /* ---- device-resident variants (bench.py's `value`: inputs already in HBM) ----------------------------- */

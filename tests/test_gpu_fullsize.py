@@ -62,19 +62,22 @@ def _certificate(pr, d, delta, lp, p, lam):
     return pviol / scale, sign_bad, pobj, dobj, dres, strict
 
 
-@pytest.mark.parametrize("name,eps", [("case1354pegase", 2e-7), ("case13659pegase", 5e-7)])
-def test_full_size_certificate(gpu, name, eps):
+@pytest.mark.parametrize("name,eps,engine", [("case1354pegase", 2e-7, 0), ("case13659pegase", 5e-7, 0),
+                                             ("case1354pegase", 2e-7, 5)])
+def test_full_size_certificate(gpu, name, eps, engine):
+    """engine 0: the barrier engine (default); engine 5: the PDHG engines (stream / group hybrid)."""
     from activesetmethods_b200.sublp import SubLp
     pr = problem(name)
     d = _first_linearisation(pr)
     delta = 1000.0
-    lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, eps_rel=eps, max_iter=8_000_000)
+    lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, eps_rel=eps, max_iter=8_000_000, engine=engine)
     p, lam, mu_u, mu_l, slack, status = lp.sub_optimize(d["x"], d["f"], d["df"], d["E"], d["dE"], delta, False)
     info = lp.last_info[0]
     assert status == 0, info
     pviol, sign_bad, pobj, dobj, dres, strict = _certificate(pr, d, delta, lp, p, lam)
     gap = abs(pobj - dobj) / (1.0 + abs(pobj) + abs(dobj))
-    print(f"{name}: {info['iterations']} PDHG iterations ({lp.engine_info()}), objective {pobj + d['f']:.6f}, "
+    assert lp.engine_info()["engine"] == (4 if engine == 0 else 2)
+    print(f"{name}: {info['iterations']} iterations ({lp.engine_info()}), objective {pobj + d['f']:.6f}, "
           f"relative primal violation {pviol:.2e}, dual residual {dres:.2e}, gap {gap:.2e}; strict lower bound "
           f"{strict + d['f']:.4f} (certified relative gap {abs(pobj - strict) / max(1.0, abs(pobj)):.1e})")
     assert pviol <= 1e-6 and sign_bad <= 1e-9
@@ -95,21 +98,24 @@ def test_full_size_certificate(gpu, name, eps):
     lp.close()
 
 
-def test_full_size_batch_matches_single(gpu):
-    """A 64-scenario case1354 batch (streaming kernels, then the group kernel for the stragglers): every scenario's
-    objective equals what the single-LP engine gives for it (two engines, same optimum), and all are optimal."""
+@pytest.mark.parametrize("engine", [0, 5])
+def test_full_size_batch_matches_single(gpu, engine):
+    """A 64-scenario case1354 batch: every scenario's objective equals what a single-LP handle gives for it, and all are
+    optimal.  engine 0: barrier engine, scenarios across the lanes of a warp vs. one LP with the terms across the
+    threads; engine 5: PDHG streaming kernels, then the group kernel for the stragglers, vs. the group kernel alone."""
     import bench
     from activesetmethods_b200.sublp import SubLp
     net = bench.network("case1354pegase")
     S = 64
     mdl, d = bench.linearise(net, list(range(1, S + 1)))
-    lpb = SubLp(mdl.n, mdl.m, mdl.j_str, d["xL"], d["xU"], d["gL"], d["gU"], batch=S, eps_rel=5e-7, max_iter=8_000_000)
+    lpb = SubLp(mdl.n, mdl.m, mdl.j_str, d["xL"], d["xU"], d["gL"], d["gU"], batch=S, eps_rel=5e-7, max_iter=8_000_000, engine=engine)
     out = lpb.sub_optimize(d["x"], d["f"], d["df"], d["E"], d["dE"], 1000.0, False)
     assert np.all(out[5] == 0)
     objs = np.array([i["objective"] for i in lpb.last_info])
-    assert lpb.engine_info()["engine"] == 3          # streamed, then handed over
+    assert lpb.engine_info()["engine"] == (4 if engine == 0 else 3)          # 3: streamed, then handed over
     for s in (0, 17, 63):
-        lp1 = SubLp(mdl.n, mdl.m, mdl.j_str, d["xL"][s], d["xU"][s], d["gL"][s], d["gU"][s], eps_rel=5e-7, max_iter=8_000_000)
+        lp1 = SubLp(mdl.n, mdl.m, mdl.j_str, d["xL"][s], d["xU"][s], d["gL"][s], d["gU"][s], eps_rel=5e-7, max_iter=8_000_000,
+                    engine=engine)
         lp1.sub_optimize(d["x"][s], d["f"][s], d["df"][s], d["E"][s], d["dE"][s], 1000.0, False)
         o1 = lp1.last_info[0]["objective"]
         assert lp1.last_info[0]["status"] == 0

@@ -245,7 +245,7 @@ def test_large_batch_with_compaction(gpu):
     df = np.array([m.eval_grad_f(xx, np.zeros(m.n)) for m, xx in zip(mdls, x)])
     E = np.array([m.eval_g(xx, np.zeros(m.m)) for m, xx in zip(mdls, x)])
     dE = np.array([m.eval_jac_g(xx, "eval", None, None, np.zeros(m.nnz)) for m, xx in zip(mdls, x)])
-    lpb = SubLp(m0.n, m0.m, m0.j_str, xL, xU, gL, gU, batch=B, eps_rel=1e-7)
+    lpb = SubLp(m0.n, m0.m, m0.j_str, xL, xU, gL, gU, batch=B, eps_rel=1e-7, engine=5)     # PDHG hybrid
     pb, lamb, _, _, _, stb = lpb.sub_optimize(x, f, df, E, dE, 1000.0, False)
     assert np.all(stb == 0)
     objs = np.array([i["objective"] for i in lpb.last_info])
