@@ -265,8 +265,8 @@ def case9() -> Network:
 # Synthetic networks with the pegase shapes (the real files are not shipped with the reference)
 # ----------------------------------------------------------------------------------------------------------
 def synthetic_network(nb: int, ng: int, nl: int, seed: int | None = None) -> Network:
-    """Seeded random network: spanning tree + extra local edges, log-normal impedances, loads on ~60 % of
-    buses, generation capacity 1.8x load, quadratic costs, thermal ratings from a DC power flow
+    """Seeded random network: spanning tree + extra local edges (plus a few long ties above 5000 buses, see below),
+    log-normal impedances, loads on ~60 % of buses, generation capacity 1.8x load, quadratic costs, thermal ratings from a DC power flow
     (SURVEY.md §8(d) recipe).  ``seed`` defaults to the bus count."""
     rng = np.random.default_rng(nb if seed is None else seed)
     assert nl >= nb - 1
@@ -280,6 +280,12 @@ def synthetic_network(nb: int, ng: int, nl: int, seed: int | None = None) -> Net
     extra = nl - (nb - 1)
     a = rng.integers(0, nb, size=extra)
     off = rng.integers(2, 40, size=extra)
+    if nb >= 5000:
+        # continental grids have an extra-high-voltage backbone: without long ties the local windows above give a
+        # chain-like graph whose hop diameter grows like nb / 35 (390 hops for 13 659 buses, against ~50 for the real
+        # European cases); 2 % of the extra branches become ties of log-uniform length up to a quarter of the network
+        long_tie = rng.random(extra) < 0.02
+        off = np.where(long_tie, np.exp(rng.uniform(math.log(40.0), math.log(nb / 4.0), extra)).astype(np.int64), off)
     b = (a + off) % nb
     f[nb - 1:] = np.minimum(a, b)
     t[nb - 1:] = np.maximum(a, b)

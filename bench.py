@@ -10,8 +10,9 @@ the multiplier read-back with the reference's masking, the violation norm and th
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU; torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle's HiGHS simplex on all host cores
 
-Per-GPU work is fixed (``--scenarios`` per GPU, default 128 so that N = 8 is the 1024-scenario config):
-weak scaling.  One JSON line is printed by rank 0.
+The job is fixed (``--scenarios``, default 1024 = BASELINE config 5) and split over the GPUs: strong scaling.  At
+N = 1 the line also carries BASELINE's single-instance figures (sub-LP ms and SLP iterations/s on case13659pegase)
+under ``single_instance``.  One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -41,11 +42,15 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--case", default="case1354pegase")
-    ap.add_argument("--scenarios", type=int, default=128, help="scenarios per GPU")
+    ap.add_argument("--scenarios", type=int, default=1024,
+                    help="scenarios of the whole job (BASELINE config 5: 1024), split over the GPUs")
+    ap.add_argument("--single-case", default="case13659pegase",
+                    help="instance of the single-instance metrics reported at N = 1 (sub-LP ms, SLP it/s); 'none' skips them")
+    ap.add_argument("--single-slp-iters", type=int, default=12)
     ap.add_argument("--eps", type=float, default=5e-7,
                     help="relative KKT tolerance; 5e-7 keeps |pobj - dobj| / |obj| below the 1e-6 parity bar")
     ap.add_argument("--delta", type=float, default=1000.0, help="step bound (Line Search uses 1000, slp.jl:23)")
-    ap.add_argument("--engine", type=int, default=0)
+    ap.add_argument("--engine", type=int, default=0, help="0 / 4 barrier engine, 5 PDHG hybrid, 1 / 2 PDHG streaming / group")
     ap.add_argument("--max-iter", type=int, default=4_000_000)
     ap.add_argument("--cpu-sample", type=int, default=2, help="scenarios of the cpu_baseline sample")
     ap.add_argument("--ref-sample", type=int, default=0, help="scenarios per reference step (0 = one per core)")
@@ -191,7 +196,7 @@ def run_reference(a):
               f"core), host NLP evaluation included in the step")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * t_total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": 1e3 * t_total / a.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{a.case} load scenarios, first SLP linearisation, sub-LP to simplex tolerance 1e-9",
                    "scenarios_per_step": per_step, "delta": a.delta, "optimal": n_ok},
@@ -204,6 +209,63 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
+def kkt_bytes(st, B):
+    """Algorithmic bytes of one numeric factorisation and of one substitution pair of a batch of B LPs (DESIGN.md
+    section 4.4): f64 operands the fan-out schedule has to move per scenario, plus the index lists, which a warp reads
+    once for its 32 scenarios."""
+    terms, fch, wch, nnzL, N = st["terms"], st["factor_chunks"], st["forward_chunks"], st["nnz_L"], st["kkt_dim"]
+    per_lp_factor = 24 * terms + 16 * fch + 8 * nnzL + 16 * N        # W[a], W[b], 1/d[k]; target read+write; clear; pivots
+    idx_factor = 16 * terms + 4 * fch
+    per_lp_pair = (24 * nnzL + 16 * wch) + 24 * N + 40 * nnzL        # forward items + targets; diagonal pass; backward
+    idx_pair = 16 * nnzL + 4 * wch + 16 * nnzL
+    warps = max(1, B // 32)
+    return B * per_lp_factor + warps * idx_factor, B * per_lp_pair + warps * idx_pair
+
+
+def single_instance(a, local):
+    """BASELINE's first metric on its own config: sub-LP ms and SLP iterations/s on case13659pegase (one GPU)."""
+    from activesetmethods_b200.slp import Model, Parameters, SlpLS
+    from activesetmethods_b200.sublp import SubLp
+    from activesetmethods_b200.examples import acopf
+    t0 = time.perf_counter()
+    net = network(a.single_case)
+    mdl = acopf.AcopfModel(net)
+    t_model = time.perf_counter() - t0
+    x = np.clip(mdl.x0, mdl.x_L, mdl.x_U)
+    args = (x, mdl.eval_f(x), mdl.eval_grad_f(x, np.zeros(mdl.n)), mdl.eval_g(x, np.zeros(mdl.m)),
+            mdl.eval_jac_g(x, "eval", None, None, np.zeros(mdl.nnz)), a.delta, False)
+    t0 = time.perf_counter()
+    lp = SubLp(mdl.n, mdl.m, mdl.j_str, mdl.x_L, mdl.x_U, mdl.g_L, mdl.g_U, device=local, eps_rel=a.eps, engine=a.engine)
+    lp.sub_optimize(*args)                                   # first call: symbolic analysis + graph capture
+    t_first = time.perf_counter() - t0
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        out = lp.sub_optimize(*args)
+        times.append(time.perf_counter() - t0)
+    info = lp.last_info[0]
+    loop_ms, its = lp.last_solve_timing()
+    st = lp.ipm_info() if lp.engine_info()["engine"] == 4 else {}
+    lp.close()
+    # SLP line search (reference defaults: tolerances 1e-2, Delta = 1000) with the device-side NLP evaluator
+    prm = Parameters(algorithm="Line Search", max_iter=a.single_slp_iters, device=local, device_evaluator=True,
+                     lp_options=dict(eps_rel=a.eps, engine=a.engine))
+    slp = SlpLS(Model.from_problem(mdl, prm))
+    t0 = time.perf_counter()
+    slp.run()
+    t_slp = time.perf_counter() - t0
+    n_lp = len(slp.lp_log)
+    return {"case": a.single_case, "n": mdl.n, "m": mdl.m, "nnz_coo": mdl.nnz,
+            "sub_lp_ms": 1e3 * float(np.median(times)), "sub_lp_device_ms": loop_ms, "sub_lp_status": int(out[5]),
+            "sub_lp_objective": info["objective"], "sub_lp_newton_steps": int(info["iterations"]),
+            "first_call_s": t_first, "symbolic_ms": st.get("symbolic_ms"), "kkt": st,
+            "slp_iter_per_s": slp.iter / t_slp, "slp_iterations": int(slp.iter), "slp_sub_lps": n_lp,
+            "slp_status": int(slp.ret), "slp_objective": float(slp.obj_val), "slp_violation": float(slp.prim_infeas),
+            "slp_wall_s": t_slp, "slp_lp_statuses": sorted(set(int(e[0]) for e in slp.lp_log)),
+            "note": f"Line Search, reference tolerances (1e-2), at most {a.single_slp_iters} SLP iterations, device-side "
+                    f"ACOPF evaluator; host model build {t_model:.1f} s not included"}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -225,10 +287,13 @@ def run_ours(a):
         raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
 
-    S = a.scenarios
+    total_scen = a.scenarios
     net = network(a.case)
-    ids = shard.scenario_ids(rank, world, S)             # scenario id = seed
+    ids = shard.split_scenarios(total_scen, world)[rank]     # strong scaling: contiguous blocks of scenario ids (= seeds)
+    S = len(ids)
+    t0 = time.perf_counter()
     mdl, d = linearise(net, ids)
+    t_host_eval = time.perf_counter() - t0
     n, m, nnz = mdl.n, mdl.m, mdl.nnz
     lp = SubLp(n, m, mdl.j_str, d["xL"], d["xU"], d["gL"], d["gU"], batch=S, device=local, eps_rel=a.eps,
                engine=a.engine, max_iter=a.max_iter)
@@ -243,7 +308,7 @@ def run_ours(a):
     hdelta = pinned((S,))
     hdelta[...] = a.delta
     hout = dict(p=pinned((S, n)), lam=pinned((S, m)), mu_u=pinned((S, n)), mu_l=pinned((S, n)),
-                slack=pinned((S, m, 2)), viol=pinned((S,)), deriv=pinned((S,)))
+                slack=pinned((S, m, 2)), viol=pinned((S,)), deriv=pinned((S,)), nu=pinned((S, m)))
     hstatus = torch.empty(S, dtype=torch.int32).pin_memory().numpy()
     info = (capi.LpInfo * S)()
     P = capi.dptr
@@ -255,8 +320,8 @@ def run_ours(a):
             C.byref(lp.params), P(hout["p"]), P(hout["lam"]), P(hout["mu_u"]), P(hout["mu_l"]), P(hout["slack"]),
             hstatus.ctypes.data_as(capi.c_int32_p), info))
         capi.check(lib.asm_slp_norm_violations(lp._h, None, None, 0, P(hout["viol"])))
-        nu = np.abs(hout["lam"])                              # compute_nu!, slp_line_search.jl:251-261
-        capi.check(lib.asm_slp_merit_derivative(lp._h, P(nu), 0, P(hout["deriv"])))
+        np.abs(hout["lam"], out=hout["nu"])                   # compute_nu!, slp_line_search.jl:251-261
+        capi.check(lib.asm_slp_merit_derivative(lp._h, P(hout["nu"]), 0, P(hout["deriv"])))
 
     def resident_step():
         """Same work with x_k, df, E, dE already in HBM: device time from CUDA events on the handle's stream."""
@@ -279,9 +344,19 @@ def run_ours(a):
     def sum_over_ranks(x):
         return shard.sum_over_ranks(x, device="cuda" if world > 1 else None)
 
+    # ---- warm-up: full steps (the first one runs the symbolic analysis and captures the CUDA graphs)
+    lp.update(hin["x"], hin["f"], hin["df"], hin["E"], hin["dE"], hdelta, False)   # inputs resident
+    t0 = time.perf_counter()
+    resident_step()
+    t_first = time.perf_counter() - t0
+    for _ in range(max(0, a.warmup - 2)):
+        resident_step()
+    e2e_step()
+    eng = lp.engine_info()
+    kst = lp.ipm_info() if eng["engine"] == 4 else None
     # timing rule: inputs larger than L2, or flush L2 between timed steps (outside the timed region)
-    Bpad0 = 1 if S <= 1 else (32 if S <= 32 else ((S + 63) // 64) * 64)
-    working_set = Bpad0 * (16 * nnz_csr + 64 * n + 48 * m)
+    Bpad = 1 if S <= 1 else (32 if S <= 32 else ((S + 63) // 64) * 64)
+    working_set = Bpad * (8 * (kst["nnz_L"] + 2 * kst["kkt_dim"]) if kst else (16 * nnz_csr + 64 * n + 48 * m))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if working_set < 2 * (126 << 20) else None
 
     def flush_l2():
@@ -289,9 +364,7 @@ def run_ours(a):
             flush_buf.zero_()
             torch.cuda.synchronize()
 
-    lp.update(hin["x"], hin["f"], hin["df"], hin["E"], hin["dE"], hdelta, False)   # inputs resident
-    for _ in range(a.warmup):
-        resident_step()
+    # ---- timed, inputs resident in HBM: CUDA events on the handle's stream
     clocks = ClockSampler(local)
     sync_all()
     clocks.start()
@@ -304,59 +377,74 @@ def run_ours(a):
     sync_all()
     wall_resident = time.perf_counter() - t0
     launches = lp.launch_count() - l0
-    infos = [dict(status=int(i.status), iterations=int(i.iterations), objective=float(i.objective)) for i in info[:S]]
+    infos = [dict(status=int(i.status), iterations=int(i.iterations), objective=float(i.objective),
+                  pres=float(i.primal_residual), dres=float(i.dual_residual), gap=float(i.gap)) for i in info[:S]]
     loop_ms, loop_its = lp.last_solve_timing()
-    eng = lp.engine_info()
     dev_s = max_over_ranks(dev_ms * 1e-3)
-    # ---- end to end through the C ABI with pinned host buffers
-    e2e_steps = min(a.steps, 2)            # each step is a full cold solve of the batch: two are enough
-    e2e_step()
+    # ---- timed, end to end through the C ABI with pinned host buffers (same number of steps)
     sync_all()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_wall = 0.0
+    for _ in range(a.steps):
+        flush_l2()
+        sync_all()
+        t0 = time.perf_counter()
         e2e_step()
-    sync_all()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+        torch.cuda.synchronize()
+        e2e_wall += time.perf_counter() - t0
+    e2e_s = max_over_ranks(e2e_wall)
     clk = clocks.stop()
     n_opt = sum_over_ranks(float(sum(1 for i in infos if i["status"] == 0)))
     its_max = max_over_ranks(float(max(i["iterations"] for i in infos)))
     its_sum = sum_over_ranks(float(sum(i["iterations"] for i in infos)))
-    total_scen = S * world
     value = total_scen * a.steps / dev_s
-    e2e = total_scen * e2e_steps / e2e_s
+    e2e = total_scen * a.steps / e2e_s
     h2d = 8 * S * (2 * n + m + nnz + 2) + 8 * S * m          # sub_optimize inputs + nu
     d2h = 8 * S * (3 * n + m + 2 * m) + 4 * S + 8 * S * 2    # p, lambda, mu_U, mu_L, slacks, status, 2 merit scalars
 
-    # ---- roofline of the dominant kernels: the streaming PDHG iteration pair, measured live
-    pm, dm = lp.kernel_timing(50)
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the handle's stream
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    Bp = lp.params  # noqa: F841
-    Bpad = 1 if S <= 1 else (32 if S <= 32 else ((S + 63) // 64) * 64)   # pad_batch() of csrc/util.cuh
-    by_primal = Bpad * (8 * nnz_csr + 8 * m + 56 * n) + 4 * nnz_csr + 4 * (n + 1)
-    by_dual = Bpad * (8 * nnz_csr + 8 * n + 40 * m) + 4 * nnz_csr + 4 * (m + 1)
-    achieved = (by_primal + by_dual) / ((pm + dm) * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(f"{a.case}:{S}")
-        except (OSError, ValueError):
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
-                "kernel": "k_primal2 + k_dual2 (one PDHG iteration of the whole batch; k_primal/k_dual<batch> "
-                          "when the padded batch is not a multiple of 64)",
-                "bytes_per_launch_pair": by_primal + by_dual, "primal_ms": pm, "dual_ms": dm,
-                "primal_gbs": by_primal / (pm * 1e-3) / 1e9, "dual_gbs": by_dual / (dm * 1e-3) / 1e9,
-                "loop_ms_per_iteration": loop_ms / max(loop_its, 1)}
+    if kst is not None:
+        fac_ms, pair_ms = lp.ipm_timing(10)
+        by_fac, by_pair = kkt_bytes(kst, Bpad)
+        newton = its_sum / total_scen
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(f"k_ldl_factor:{a.case}:{S}")
+            except (OSError, ValueError):
+                traffic = None
+        achieved = by_fac / (fac_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic,
+                    "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+                    "kernel": "k_ldl_factor: one numeric L D L' of the KKT matrices of the whole batch (one launch per "
+                              "level of the elimination tree, replayed as a CUDA graph)",
+                    "bytes_per_launch": by_fac, "factor_ms": fac_ms, "launches_per_factorisation": kst["launches_factor"],
+                    "substitution_pair_ms": pair_ms, "substitution_pair_bytes": by_pair,
+                    "substitution_pair_gbs": by_pair / (pair_ms * 1e-3) / 1e9,
+                    "newton_steps_mean": newton, "kkt": kst,
+                    "share_of_step": {"factor": newton * fac_ms / (1e3 * dev_s / a.steps),
+                                      "substitutions": newton * 2 * (1 + lp.params.ipm_refine) * pair_ms / (1e3 * dev_s / a.steps)}}
+    else:
+        pm, dm = lp.kernel_timing(50)
+        by_primal = Bpad * (8 * nnz_csr + 8 * m + 56 * n) + 4 * nnz_csr + 4 * (n + 1)
+        by_dual = Bpad * (8 * nnz_csr + 8 * n + 40 * m) + 4 * nnz_csr + 4 * (m + 1)
+        achieved = (by_primal + by_dual) / ((pm + dm) * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None,
+                    "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+                    "kernel": "k_primal2 + k_dual2 (one PDHG iteration of the whole batch)",
+                    "bytes_per_launch_pair": by_primal + by_dual, "primal_ms": pm, "dual_ms": dm,
+                    "loop_ms_per_iteration": loop_ms / max(loop_its, 1)}
 
     cpu = None
+    single = None
     if rank == 0 and world == 1 and a.cpu_sample > 0:
         cpu = cpu_baseline(a.case, a.delta, a.cpu_sample)
         # the same scenarios on the GPU against the checker: relative objective difference (parity bar 1e-6)
@@ -364,29 +452,39 @@ def run_ours(a):
                 for s, obj in enumerate(cpu.pop("objectives")) if obj is not None and infos[s]["status"] == 0]
         cpu["gpu_objective_rel_diff_max"] = max(rels) if rels else None
         cpu["gpu_objective_parity_1e-6"] = bool(rels) and max(rels) <= 1e-6
+    lp.close()
+    if rank == 0 and world == 1 and a.single_case != "none":
+        single = single_instance(a, local)
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * dev_s / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{S} load-perturbed {a.case} scenarios per GPU ({total_scen} total; 8 GPUs = the "
-                                   f"1024-scenario config), first SLP linearisation, Line Search step bound {a.delta:g}",
+            "config": {"workload": f"{total_scen} load-perturbed {a.case} scenarios (BASELINE config 5), split over the "
+                                   f"GPUs ({S} on rank 0), first SLP linearisation, Line Search step bound {a.delta:g}",
+                       "scenarios_total": total_scen, "scenarios_per_gpu": S,
                        "n": n, "m": m, "nnz_coo": nnz, "nnz_csr": nnz_csr, "eps_rel": a.eps,
-                       "engine": eng, "optimal": int(n_opt), "pdhg_iterations_max": int(its_max),
-                       "pdhg_iterations_mean": its_sum / total_scen,
-                       "l2": ("no flush: the batch working set (%.0f MB per iteration) exceeds the 126 MB L2"
+                       "engine": eng, "optimal": int(n_opt), "lp_iterations_max": int(its_max),
+                       "lp_iterations_mean": its_sum / total_scen,
+                       "worst_relative_residuals": {
+                           "primal": max(i["pres"] for i in infos), "dual": max(i["dres"] for i in infos),
+                           "gap": max(i["gap"] / (1.0 + 2.0 * abs(i["objective"])) for i in infos)},
+                       "warmup_steps": f"{a.warmup} full steps ({max(0, a.warmup - 1)} resident + 1 end-to-end); the first "
+                                       f"one ({t_first:.2f} s) includes the symbolic analysis and the CUDA-graph capture",
+                       "l2": ("no flush: the factorisation working set (%.0f MB) exceeds the 126 MB L2"
                               if flush_buf is None else
-                              "working set %.0f MB per iteration: L2 flushed between timed steps by writing 256 MB")
+                              "working set %.0f MB: L2 flushed between timed steps by writing 256 MB")
                              % (working_set / 1e6),
-                       "wall_s_resident": wall_resident},
+                       "host_nlp_evaluation_s": t_host_eval, "wall_s_resident": wall_resident},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": a.steps, "ms_per_step": 1e3 * e2e_s / a.steps},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clk,
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
+        if single is not None:
+            out["single_instance"] = single
         print(json.dumps(out), flush=True)
-    lp.close()
     if world > 1:
         dist.destroy_process_group()
 

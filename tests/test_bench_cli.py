@@ -25,7 +25,7 @@ def test_reference_arm_json_line():
     assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["optimal"] == 4 and "workload" in d["config"] and d["scaling"] == "weak" and d["dtype"] == "f64"
+    assert d["config"]["optimal"] == 4 and "workload" in d["config"] and d["scaling"] == "strong" and d["dtype"] == "f64"
 
 
 def test_reference_arm_other_ranks_exit_quietly():

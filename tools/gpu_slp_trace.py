@@ -10,11 +10,15 @@ from activesetmethods_b200.slp import Model, Parameters, SlpLS, SlpTR
 name, a = sys.argv[1], sys.argv[2]
 tight = len(sys.argv) > 3 and sys.argv[3] == "tight"
 opts = {}
+extra = {}
 for kv in sys.argv[4:]:
     k, v = kv.split("=")
+    if k in ("device_evaluator", "max_iter"):
+        extra[k] = int(v)
+        continue
     opts[k] = float(v) if ("." in v or "e" in v) else int(v)
 tol = dict(tol_residual=1e-8, tol_infeas=1e-8) if tight else {}
-mdl = Model.from_problem(problem(name), Parameters(algorithm={"LS": "Line Search", "TR": "Trust Region"}[a], max_iter=300, lp_options=opts, **tol))
+mdl = Model.from_problem(problem(name), Parameters(algorithm={"LS": "Line Search", "TR": "Trust Region"}[a], lp_options=opts, **{'max_iter': 300, **extra}, **tol))
 slp = (SlpLS if a == "LS" else SlpTR)(mdl)
 orig = slp.sub_optimize
 def traced(*args, **kw):
@@ -24,5 +28,8 @@ def traced(*args, **kw):
           f"delta {getattr(slp, 'delta', 0):.3e} prim {slp.prim_infeas:.3e} dual {slp.dual_infeas:.3e} compl {slp.compl:.3e} f {slp.f:.9f}", flush=True)
     return out
 slp.sub_optimize = traced
+import time
+t0 = time.time()
 slp.run()
+print("wall", time.time() - t0)
 print("ret", slp.ret, "iter", slp.iter, "obj", slp.obj_val)
