@@ -930,7 +930,7 @@ void asm_lp_default_params(asm_lp_params *p) {
     p->group_size = 0;
     p->hand_over = 0.5;
     p->ipm_max_iter = 200;
-    p->ipm_refine = 2;
+    p->ipm_refine = 1;
     p->ipm_reg = 1e-8;
     p->ipm_prox = 1e-7;
 }
@@ -1570,8 +1570,9 @@ int asm_slp_kernel_timing(asm_slp *h, int32_t reps, double *primal_ms, double *d
     return h->h.cur()->time_streaming_kernels(reps, primal_ms, dual_ms);
 }
 
-// sizes of the barrier engine's factorisation (stats[8]: KKT dimension, nnz(L), update terms, levels, factor chunks,
-// forward chunks, launches per factorisation, launches per substitution pair) and (times[4]) symbolic analysis ms,
+// sizes of the barrier engine's factorisation (stats[10]: KKT dimension, nnz(L), update terms, levels, factor chunks,
+// forward chunks, launches per factorisation, launches per substitution pair, factorisations and substitution pairs of
+// the last solve) and (times[4]) symbolic analysis ms,
 // Newton steps of the last solve, factor / solve ms of the traced step (ASM_TRACE)
 int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times) {
     if (!h) return fail(ASM_E_INVALID, "null handle");
@@ -1584,9 +1585,11 @@ int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times) {
         stats[2] = E.sym.nterms;
         stats[3] = E.sym.n_levels;
         stats[4] = E.n_fchunks;
-        stats[5] = (int64_t)E.sym.wchunk.size() - 1;
+        stats[5] = E.sym.n_wchunks;
         stats[6] = E.launches_factor;
         stats[7] = E.launches_solve;
+        stats[8] = E.last_factorisations;
+        stats[9] = E.last_pairs;
     }
     if (times) {
         times[0] = E.symbolic_ms;
@@ -1627,8 +1630,7 @@ int asm_kkt_selftest(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, con
     S.solve_host(W, invd, v);
     std::copy(v.begin(), v.end(), rhs_sol);
     if (stats) {
-        int64_t longest = 0;
-        for (size_t c = 0; c + 1 < S.fchunk.size(); ++c) longest = std::max<int64_t>(longest, S.fchunk[c + 1] - S.fchunk[c]);
+        const int64_t longest = std::max(1, S.longest_chunk);
         stats[0] = S.nnzL;
         stats[1] = S.nterms;
         stats[2] = S.n_levels;
@@ -1636,7 +1638,7 @@ int asm_kkt_selftest(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, con
         stats[4] = (int64_t)S.wlaunch.size();
         stats[5] = (int64_t)S.blaunch.size();
         stats[6] = longest;
-        stats[7] = (int64_t)S.fchunk.size() - 1;
+        stats[7] = S.n_fchunks;
     }
     return ASM_OK;
 }

@@ -51,14 +51,17 @@ struct IpmState {
     double mu, smu, ap, ad, qs, q_un;
     double ray_obj, ray_kty;  // Farkas test of the last step direction dy (normalised)
     double kept[5];           // pobj, dobj, pres, dres, gap of the point kept by k_ipm_save
+    double pres_prev, dres_prev;  // residuals of the previous step (to judge the accuracy of the linear solves)
     int ncomp, hits, acc_hits, save, bad;
 };
 
 struct KktDev {
     const KktTerm *terms;
-    const int *fchunk, *fstep;
+    const int *fs_beg, *fs_end, *fmstep;
+    const KktRange *fmchunk;
     const KktFwdItem *fwd;
-    const int *wchunk, *wstep;
+    const int *ws_beg, *ws_end, *wmstep;
+    const KktRange *wmchunk;
     const KktBwdItem *bwd;
     const int *bstep;
     const int *perm, *inv, *kmap;
@@ -74,6 +77,7 @@ struct IpmView {
     // KKT vectors (node order: columns then rows)
     double *rhs0, *sol, *work;
     IpmState *ist;
+    int *need_refine;     // scenarios whose last step did not reduce the residuals as an exact Newton step would
     const double *c0;     // objective constants (the termination test is relative to the objective the caller sees)
     double delta, prox;
     double eps, eps_acc;  // target tolerance; acceptable tolerance (kept as a fall-back result when the target is not reached)
@@ -87,10 +91,24 @@ __device__ __forceinline__ double ipm_slack(double d) { return fmax(d, 1e-30); }
 
 // =================================== numeric L D L' ============================================================
 // Step l applies the updates of the columns of level l to their targets (fan-out).  A chunk = the terms of one target
-// in this step; BATCH: a warp owns a chunk and its lanes are 32 scenarios (index loads warp-uniform, value loads
-// coalesced); single LP: a thread owns a chunk.  Exactly one thread writes a target in a step and the terms of a
-// chunk are added in ascending k: bit-reproducible.  FUSED: gridDim.x == 1 and the block walks the steps [l0, l1)
-// with a barrier in between (W, invd and diag0 are read and written by the same kernel: plain loads).
+// in this step.  Nine chunks in ten are a single term: they are stored first, and a warp keeps four of them in flight
+// (the kernel is bound by the latency of its dependent loads -- index, then operands -- not by bandwidth: ncu shows
+// 40 long-scoreboard stall cycles per issue without the pipelining).  BATCH: a warp owns a chunk and its lanes are 32
+// scenarios (index loads warp-uniform, value loads coalesced); single LP: a thread owns a chunk.  Exactly one thread
+// writes a target in a step and the terms of a chunk are added in ascending k: bit-reproducible.  FUSED: gridDim.x == 1
+// and the block walks the steps [l0, l1) with a barrier in between (W, invd and diag0 are read and written by the
+// same kernel: plain loads, no read-only path).
+__device__ __forceinline__ void ldl_apply(const KktDev &d, int tflag, double acc, int B, int s) {
+    const int t = tflag & ~kLastBit;
+    if (t >= d.nnzL) {
+        const int64_t e = (int64_t)(t - d.nnzL) * B + s;
+        const double piv = d.diag0[e] - acc;
+        d.diag0[e] = piv;
+        if (tflag & kLastBit) d.invd[e] = 1.0 / piv;
+    } else {
+        d.W[(int64_t)t * B + s] -= acc;
+    }
+}
 template <bool BATCH, bool FUSED>
 __global__ void __launch_bounds__(kThreads) k_ldl_factor(KktDev d, int B, int l0, int l1, const ScenState *st) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -99,33 +117,65 @@ __global__ void __launch_bounds__(kThreads) k_ldl_factor(KktDev d, int B, int l0
     const int first = BATCH ? blockIdx.x * kWarps + warp : blockIdx.x * kThreads + threadIdx.x;
     const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
     for (int l = l0; l < l1; ++l) {
-        const int c1 = d.fstep[l + 1];
-        if (live)
-            for (int c = d.fstep[l] + first; c < c1; c += stride) {
-                int q = d.fchunk[c];
-                const int q1 = d.fchunk[c + 1];
-                KktTerm u = d.terms[q];
-                const bool last = u.t & kLastBit;
-                const int t = u.t & ~kLastBit;
+        if (live) {
+            const int q1 = d.fs_end[l];
+            if (BATCH) {
+                for (int q = d.fs_beg[l] + 4 * first; q < q1; q += 4 * stride) {
+                    KktTerm u[4];
+                    double a[4], b[4], c[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) u[i] = d.terms[q + i < q1 ? q + i : q];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        a[i] = d.W[(int64_t)u[i].a * B + s];
+                        b[i] = d.W[(int64_t)u[i].b * B + s];
+                        c[i] = d.invd[(int64_t)u[i].k * B + s];
+                    }
+                    double tv[4];
+                    int64_t te[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int t = u[i].t & ~kLastBit;
+                        const bool piv = t >= d.nnzL;
+                        te[i] = (int64_t)(piv ? t - d.nnzL : t) * B + s;
+                        tv[i] = piv ? d.diag0[te[i]] : d.W[te[i]];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (q + i >= q1) break;
+                        const double r = tv[i] - a[i] * b[i] * c[i];
+                        if ((u[i].t & ~kLastBit) >= d.nnzL) {
+                            d.diag0[te[i]] = r;
+                            if (u[i].t & kLastBit) d.invd[te[i]] = 1.0 / r;
+                        } else {
+                            d.W[te[i]] = r;
+                        }
+                    }
+                }
+            } else {
+                for (int q = d.fs_beg[l] + first; q < q1; q += stride) {
+                    const KktTerm u = d.terms[q];
+                    ldl_apply(d, u.t, d.W[u.a] * d.W[u.b] * d.invd[u.k], 1, 0);
+                }
+            }
+            const int c1 = d.fmstep[l + 1];
+            for (int c = d.fmstep[l] + first; c < c1; c += stride) {
+                const KktRange r = d.fmchunk[c];
+                KktTerm u = d.terms[r.begin];
+                const int tflag = u.t;
                 double acc = d.W[(int64_t)u.a * B + s] * d.W[(int64_t)u.b * B + s] * d.invd[(int64_t)u.k * B + s];
-                for (++q; q < q1; ++q) {
+                for (int q = r.begin + 1; q < r.end; ++q) {
                     u = d.terms[q];
                     acc += d.W[(int64_t)u.a * B + s] * d.W[(int64_t)u.b * B + s] * d.invd[(int64_t)u.k * B + s];
                 }
-                if (t >= d.nnzL) {
-                    const int64_t e = (int64_t)(t - d.nnzL) * B + s;
-                    const double piv = d.diag0[e] - acc;
-                    d.diag0[e] = piv;
-                    if (last) d.invd[e] = 1.0 / piv;
-                } else {
-                    d.W[(int64_t)t * B + s] -= acc;
-                }
+                ldl_apply(d, tflag, acc, B, s);
             }
+        }
         if (FUSED) __syncthreads();
     }
 }
 
-// forward substitution  v <- L^-1 v  (fan-out, chunked like the factorisation; v indexed by node id, in place)
+// forward substitution  v <- L^-1 v  (fan-out, laid out like the factorisation; v indexed by node id, in place)
 template <bool BATCH, bool FUSED>
 __global__ void __launch_bounds__(kThreads) k_ldl_fwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -134,20 +184,44 @@ __global__ void __launch_bounds__(kThreads) k_ldl_fwd(KktDev d, double *v, int B
     const int first = BATCH ? blockIdx.x * kWarps + warp : blockIdx.x * kThreads + threadIdx.x;
     const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
     for (int l = l0; l < l1; ++l) {
-        const int c1 = d.wstep[l + 1];
-        if (live)
-            for (int c = d.wstep[l] + first; c < c1; c += stride) {
-                int q = d.wchunk[c];
-                const int q1 = d.wchunk[c + 1];
-                KktFwdItem u = d.fwd[q];
+        if (live) {
+            const int q1 = d.ws_end[l];
+            if (BATCH) {
+                for (int q = d.ws_beg[l] + 4 * first; q < q1; q += 4 * stride) {
+                    KktFwdItem u[4];
+                    double a[4], x[4], c[4], t[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) u[i] = d.fwd[q + i < q1 ? q + i : q];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        a[i] = d.W[(int64_t)u[i].pos * B + s];
+                        x[i] = v[(int64_t)u[i].src * B + s];
+                        c[i] = d.invd[(int64_t)u[i].k * B + s];
+                        t[i] = v[(int64_t)u[i].dst * B + s];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (q + i < q1) v[(int64_t)u[i].dst * B + s] = t[i] - a[i] * x[i] * c[i];
+                }
+            } else {
+                for (int q = d.ws_beg[l] + first; q < q1; q += stride) {
+                    const KktFwdItem u = d.fwd[q];
+                    v[u.dst] -= d.W[u.pos] * v[u.src] * d.invd[u.k];
+                }
+            }
+            const int c1 = d.wmstep[l + 1];
+            for (int c = d.wmstep[l] + first; c < c1; c += stride) {
+                const KktRange r = d.wmchunk[c];
+                KktFwdItem u = d.fwd[r.begin];
                 const int dst = u.dst;
                 double acc = d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s] * d.invd[(int64_t)u.k * B + s];
-                for (++q; q < q1; ++q) {
+                for (int q = r.begin + 1; q < r.end; ++q) {
                     u = d.fwd[q];
                     acc += d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s] * d.invd[(int64_t)u.k * B + s];
                 }
                 v[(int64_t)dst * B + s] -= acc;
             }
+        }
         if (FUSED) __syncthreads();
     }
 }
@@ -169,12 +243,31 @@ __global__ void __launch_bounds__(kThreads) k_ldl_bwd(KktDev d, double *v, int B
     const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
     for (int l = l1 - 1; l >= l0; --l) {
         const int q1 = d.bstep[l + 1];
-        if (live)
-            for (int q = d.bstep[l] + first; q < q1; q += stride) {
-                const KktBwdItem u = d.bwd[q];
-                v[(int64_t)u.dst * B + s] -=
-                    d.invd[(int64_t)u.k * B + s] * d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s];
+        if (live) {
+            if (BATCH) {
+                for (int q = d.bstep[l] + 4 * first; q < q1; q += 4 * stride) {
+                    KktBwdItem u[4];
+                    double a[4], x[4], c[4], t[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) u[i] = d.bwd[q + i < q1 ? q + i : q];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        a[i] = d.W[(int64_t)u[i].pos * B + s];
+                        x[i] = v[(int64_t)u[i].src * B + s];
+                        c[i] = d.invd[(int64_t)u[i].k * B + s];
+                        t[i] = v[(int64_t)u[i].dst * B + s];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (q + i < q1) v[(int64_t)u[i].dst * B + s] = t[i] - c[i] * a[i] * x[i];
+                }
+            } else {
+                for (int q = d.bstep[l] + first; q < q1; q += stride) {
+                    const KktBwdItem u = d.bwd[q];
+                    v[u.dst] -= d.invd[u.k] * d.W[u.pos] * v[u.src];
+                }
             }
+        }
         if (FUSED) __syncthreads();
     }
 }
@@ -293,6 +386,7 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_init_state(LpView v, IpmV
     it.save = 0;
     it.ray_obj = -1.0;
     it.ray_kty = 1.0;
+    it.pres_prev = it.dres_prev = -1.0;
     it.bad = (badc + badr) > 0.0;
     g.ist[s] = it;
     if (st->status < 0 && it.bad) {  // lb > ub or rl > ru: nothing to iterate on
@@ -395,6 +489,15 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
     st.dres = sqrt(q[I_RLP2] + q[I_RDW2]);
     st.gap = fabs(st.pobj - st.dobj);
     st.total = iter;
+    // An exact Newton step of length a leaves (1 - a) of the linear residuals.  A long step that leaves more than half
+    // of them means the linear solves are not accurate enough: ask the host for another refinement pass.
+    if (it.pres_prev >= 0.0 && iter >= 8) {   // the first steps, far from the central path, say little
+        const bool p_bad = it.ap > 0.5 && pres > 0.5 * it.pres_prev + 0.5 * g.eps * (1.0 + st.nq_un);
+        const bool d_bad = it.ad > 0.5 && dres > 0.5 * it.dres_prev + 0.5 * g.eps * (1.0 + st.nc_un);
+        if (p_bad || d_bad) atomicAdd(g.need_refine, 1);
+    }
+    it.pres_prev = pres;
+    it.dres_prev = dres;
     const double c0 = g.c0[s];
     const double gden = 1.0 + fabs(pq + c0) + fabs(dq + c0);
     auto within = [&](double e) {
@@ -827,7 +930,8 @@ struct IpmEngine {
     KktSymbolic sym;
     bool ready = false;
     int B = 0;
-    DBuf<int> fchunk, fstep, wchunk, wstep, bstep, perm, inv, kmap;
+    DBuf<int> fs_beg, fs_end, fmstep, ws_beg, ws_end, wmstep, bstep, perm, inv, kmap;
+    DBuf<KktRange> fmchunk, wmchunk;
     DBuf<KktTerm> terms;
     DBuf<KktFwdItem> fwd;
     DBuf<KktBwdItem> bwd;
@@ -838,6 +942,7 @@ struct IpmEngine {
     int64_t launches_factor = 0, launches_solve = 0;
     double symbolic_ms = 0.0;
     int last_newton = 0;
+    int64_t last_pairs = 0, last_factorisations = 0;   // substitution pairs / factorisations of the last solve
     int64_t n_fchunks = 0;
     float last_factor_ms = 0.f, last_solve_ms = 0.f;
 
@@ -867,11 +972,15 @@ struct IpmEngine {
             return fail(ASM_E_INVALID, "KKT symbolic analysis failed (index out of range or more than 2^31 update terms)");
         symbolic_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         ASM_TRY(up(terms, sym.terms));
-        ASM_TRY(up(fchunk, sym.fchunk));
-        ASM_TRY(up(fstep, sym.fstep));
+        ASM_TRY(up(fs_beg, sym.fs_beg));
+        ASM_TRY(up(fs_end, sym.fs_end));
+        ASM_TRY(up(fmstep, sym.fmstep));
+        ASM_TRY(up(fmchunk, sym.fmchunk));
         ASM_TRY(up(fwd, sym.fwd));
-        ASM_TRY(up(wchunk, sym.wchunk));
-        ASM_TRY(up(wstep, sym.wstep));
+        ASM_TRY(up(ws_beg, sym.ws_beg));
+        ASM_TRY(up(ws_end, sym.ws_end));
+        ASM_TRY(up(wmstep, sym.wmstep));
+        ASM_TRY(up(wmchunk, sym.wmchunk));
         ASM_TRY(up(bwd, sym.bwd));
         ASM_TRY(up(bstep, sym.bstep));
         ASM_TRY(up(perm, sym.perm));
@@ -881,8 +990,8 @@ struct IpmEngine {
         std::vector<KktTerm>().swap(sym.terms);
         std::vector<KktFwdItem>().swap(sym.fwd);
         std::vector<KktBwdItem>().swap(sym.bwd);
-        n_fchunks = (int64_t)sym.fchunk.size() - 1;
-        std::vector<int>().swap(sym.fchunk);
+        std::vector<KktRange>().swap(sym.fmchunk);
+        n_fchunks = sym.n_fchunks;
         const size_t N = sym.N;
         ASM_TRY(W.alloc(std::max<size_t>(sym.nnzL, 1) * B));
         ASM_TRY(invd.alloc(N * B));
@@ -898,11 +1007,15 @@ struct IpmEngine {
     KktDev dev() const {
         KktDev d;
         d.terms = terms.p;
-        d.fchunk = fchunk.p;
-        d.fstep = fstep.p;
+        d.fs_beg = fs_beg.p;
+        d.fs_end = fs_end.p;
+        d.fmstep = fmstep.p;
+        d.fmchunk = fmchunk.p;
         d.fwd = fwd.p;
-        d.wchunk = wchunk.p;
-        d.wstep = wstep.p;
+        d.ws_beg = ws_beg.p;
+        d.ws_end = ws_end.p;
+        d.wmstep = wmstep.p;
+        d.wmchunk = wmchunk.p;
         d.bwd = bwd.p;
         d.bstep = bstep.p;
         d.perm = perm.p;
@@ -942,7 +1055,8 @@ struct IpmEngine {
         if (!L.fused) {
             const int gy = B == 1 ? 1 : B / 32;
             int64_t cap = std::max<int64_t>(1, (int64_t)kMaxBlocksX * 4 / gy);
-            gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((L.items + per_block - 1) / per_block, cap));
+            const int64_t units = B == 1 ? L.items : (L.items + 3) / 4 + 1;   // batch: four single-term chunks per warp pass
+            gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((units + per_block - 1) / per_block, cap));
         }
         return dim3(gx, B == 1 ? 1 : B / 32);
     }

@@ -17,7 +17,8 @@
 //     updates of the columns of level l to all their targets (fan-out), one "chunk" = the terms of one target
 //     in that step, summed in ascending k by one thread -- no atomics, bit-reproducible, and the critical path
 //     of a step is the longest chunk (one term near the root of the tree, where a fan-in dot product would be
-//     hundreds of terms long),
+//     hundreds of terms long).  Nine chunks in ten are a single term: those are stored first in every step so
+//     that the kernel can keep four of them in flight per warp,
 //   * the same chunked fan-out lists for the forward substitution; the backward substitution needs no chunks
 //     (the rows of a column are its ancestors, which sit on distinct levels),
 //   * the launch plan (wide steps: one launch each; runs of narrow steps: one launch of a single block per 32
@@ -42,6 +43,9 @@ struct KktFwdItem {
 struct KktBwdItem {
     int pos, src, dst, k;  // v[dst] -= invd[k] * W[pos] * v[src]   (k: permuted column of dst)
 };
+struct KktRange {
+    int begin, end;
+};
 struct KktLaunch {
     int l0, l1;  // steps [l0, l1)
     int fused;   // 1: one block walks the steps; 0: l1 == l0 + 1, grid over the items of the step
@@ -57,13 +61,19 @@ struct KktSymbolic {
     std::vector<int> Lp, Li;     // columns of L (permuted numbering), rows ascending
     std::vector<int> kmap;       // CSR entry of K -> entry of L
     std::vector<int> level;      // per permuted column
-    // factorisation: terms in (source level, target, k) order; chunk c = terms [fchunk[c], fchunk[c+1]);
-    // step l = chunks [fstep[l], fstep[l+1])
+    // factorisation: terms grouped by step (= level of the source column).  Inside a step the chunks that consist of
+    // a single term come first -- terms [fs_beg[l], fs_end[l]), one independent update each, which the kernel
+    // software-pipelines four at a time -- followed by the multi-term chunks fmchunk[fmstep[l] .. fmstep[l+1]) =
+    // (begin, end) ranges of terms with a common target, summed in ascending k
     std::vector<KktTerm> terms;
-    std::vector<int> fchunk, fstep;
+    std::vector<int> fs_beg, fs_end, fmstep;
+    std::vector<KktRange> fmchunk;
+    int64_t n_fchunks = 0, n_wchunks = 0;
+    int longest_chunk = 0;
     // forward substitution, same layout
     std::vector<KktFwdItem> fwd;
-    std::vector<int> wchunk, wstep;
+    std::vector<int> ws_beg, ws_end, wmstep;
+    std::vector<KktRange> wmchunk;
     // backward substitution: items of step l = entries whose row has level l (walked downwards)
     std::vector<KktBwdItem> bwd;
     std::vector<int> bstep;
@@ -205,15 +215,21 @@ struct KktSymbolic {
             terms.resize(nterms);
             for (const KktTerm &u : tm) terms[lpos[level[u.k]]++] = u;
         }
-        chunks(terms, [&](const KktTerm &u) { return level[u.k]; }, [](const KktTerm &u) { return u.t; }, fchunk, fstep);
+        n_fchunks = regroup(terms, [&](const KktTerm &u) { return level[u.k]; }, [](const KktTerm &u) { return u.t; },
+                            fs_beg, fs_end, fmstep, fmchunk);
         {   // the last chunk of every pivot inverts it
             std::vector<int> last(N, -1);
-            for (size_t c = 0; c + 1 < fchunk.size(); ++c) {
-                const int t = terms[fchunk[c]].t;
-                if (t >= nnzL) last[t - nnzL] = (int)c;
+            for (size_t q = 0; q < terms.size(); ++q)
+                if (terms[q].t >= nnzL) last[terms[q].t - nnzL] = (int)q;   // terms of a chunk are contiguous: its first
+            for (int l = 0; l < n_levels; ++l) {                             // term carries the flag
+                for (int q = fs_beg[l]; q < fs_end[l]; ++q)
+                    if (terms[q].t >= nnzL && last[terms[q].t - nnzL] == q) terms[q].t |= kLastBit;
+                for (int c = fmstep[l]; c < fmstep[l + 1]; ++c) {
+                    const int t = terms[fmchunk[c].begin].t;
+                    if (t >= nnzL && last[t - nnzL] >= fmchunk[c].begin && last[t - nnzL] < fmchunk[c].end)
+                        terms[fmchunk[c].begin].t |= kLastBit;
+                }
             }
-            for (int j = 0; j < N; ++j)
-                if (last[j] >= 0) terms[fchunk[last[j]]].t |= kLastBit;
         }
         // ---- forward substitution: row-major items (target i, sources ascending), then by level of the source
         {
@@ -230,7 +246,8 @@ struct KktSymbolic {
             fwd.resize(nnzL);
             for (const KktFwdItem &u : rl) fwd[lpos[level[u.k]]++] = u;
         }
-        chunks(fwd, [&](const KktFwdItem &u) { return level[u.k]; }, [](const KktFwdItem &u) { return u.dst; }, wchunk, wstep);
+        n_wchunks = regroup(fwd, [&](const KktFwdItem &u) { return level[u.k]; }, [](const KktFwdItem &u) { return u.dst; },
+                            ws_beg, ws_end, wmstep, wmchunk);
         // ---- backward substitution: entry (i, j) is applied when x_i is final, i.e. at the level of its row
         {
             bstep.assign(n_levels + 1, 0);
@@ -242,29 +259,58 @@ struct KktSymbolic {
                 for (int p = Lp[k]; p < Lp[k + 1]; ++p)
                     bwd[pos[level[Li[p]]]++] = KktBwdItem{p, perm[Li[p]], perm[k], k};
         }
-        plan(fstep, narrow, flaunch);
-        plan(wstep, narrow, wlaunch);
+        auto work = [&](const std::vector<int> &sb, const std::vector<int> &se, const std::vector<int> &ms) {
+            std::vector<int> w(n_levels + 1, 0);
+            for (int l = 0; l < n_levels; ++l) w[l + 1] = w[l] + (se[l] - sb[l]) + (ms[l + 1] - ms[l]);
+            return w;
+        };
+        plan(work(fs_beg, fs_end, fmstep), narrow, flaunch);
+        plan(work(ws_beg, ws_end, wmstep), narrow, wlaunch);
         plan(bstep, narrow, blaunch);
         return 0;
     }
 
-    // chunk = maximal run of items with the same (step, target); chunk[] gets a sentinel, step[] indexes chunks
+    // chunk = maximal run of items with the same (step, target).  Reorders the items of every step (singles first) and
+    // fills the step tables; returns the number of chunks
     template <class T, class FL, class FT>
-    void chunks(const std::vector<T> &items, FL lvl, FT tgt, std::vector<int> &chunk, std::vector<int> &step) const {
-        chunk.clear();
-        step.assign(n_levels + 1, 0);
-        int prev_l = -1, prev_t = -1;
-        for (size_t q = 0; q < items.size(); ++q) {
-            const int l = lvl(items[q]), t = tgt(items[q]);
-            if (l != prev_l || t != prev_t) {
-                chunk.push_back((int)q);
-                ++step[l + 1];
-                prev_l = l;
-                prev_t = t;
+    int64_t regroup(std::vector<T> &items, FL lvl, FT tgt, std::vector<int> &sbeg, std::vector<int> &send,
+                    std::vector<int> &mstep, std::vector<KktRange> &mchunk) {
+        sbeg.assign(n_levels, 0);
+        send.assign(n_levels, 0);
+        mstep.assign(n_levels + 1, 0);
+        mchunk.clear();
+        std::vector<T> out;
+        out.reserve(items.size());
+        int64_t n_chunks = 0;
+        size_t q = 0;
+        for (int l = 0; l < n_levels; ++l) {
+            const size_t q0 = q;
+            while (q < items.size() && lvl(items[q]) == l) ++q;
+            sbeg[l] = (int)out.size();
+            // pass 1: singles
+            for (size_t a = q0; a < q;) {
+                size_t b = a + 1;
+                while (b < q && tgt(items[b]) == tgt(items[a])) ++b;
+                if (b - a == 1) out.push_back(items[a]);
+                a = b;
             }
+            send[l] = (int)out.size();
+            // pass 2: multi-item chunks
+            for (size_t a = q0; a < q;) {
+                size_t b = a + 1;
+                while (b < q && tgt(items[b]) == tgt(items[a])) ++b;
+                ++n_chunks;
+                if (b - a > 1) {
+                    mchunk.push_back(KktRange{(int)out.size(), (int)(out.size() + (b - a))});
+                    out.insert(out.end(), items.begin() + a, items.begin() + b);
+                    longest_chunk = std::max(longest_chunk, (int)(b - a));
+                }
+                a = b;
+            }
+            mstep[l + 1] = (int)mchunk.size();
         }
-        chunk.push_back((int)items.size());
-        for (int l = 0; l < n_levels; ++l) step[l + 1] += step[l];
+        items.swap(out);
+        return n_chunks;
     }
 
     void plan(const std::vector<int> &sptr, int narrow, std::vector<KktLaunch> &out) const {
@@ -297,29 +343,35 @@ struct KktSymbolic {
     void factor_host(std::vector<double> &W, std::vector<double> &diag, std::vector<double> &invd) const {
         invd.resize(N);
         for (int j = 0; j < N; ++j) invd[j] = 1.0 / diag[j];
-        for (int l = 0; l < n_levels; ++l)
-            for (int c = fstep[l]; c < fstep[l + 1]; ++c) {
-                int t = terms[fchunk[c]].t;
-                const bool last = t & kLastBit;
-                t &= ~kLastBit;
-                double acc = 0.0;
-                for (int q = fchunk[c]; q < fchunk[c + 1]; ++q) acc += W[terms[q].a] * W[terms[q].b] * invd[terms[q].k];
-                if (t >= nnzL) {
-                    diag[t - nnzL] -= acc;
-                    if (last) invd[t - nnzL] = 1.0 / diag[t - nnzL];
-                } else {
-                    W[t] -= acc;
-                }
+        auto apply = [&](int q0, int q1) {
+            int t = terms[q0].t;
+            const bool last = t & kLastBit;
+            t &= ~kLastBit;
+            double acc = 0.0;
+            for (int q = q0; q < q1; ++q) acc += W[terms[q].a] * W[terms[q].b] * invd[terms[q].k];
+            if (t >= nnzL) {
+                diag[t - nnzL] -= acc;
+                if (last) invd[t - nnzL] = 1.0 / diag[t - nnzL];
+            } else {
+                W[t] -= acc;
             }
+        };
+        for (int l = 0; l < n_levels; ++l) {
+            for (int q = fs_beg[l]; q < fs_end[l]; ++q) apply(q, q + 1);
+            for (int c = fmstep[l]; c < fmstep[l + 1]; ++c) apply(fmchunk[c].begin, fmchunk[c].end);
+        }
     }
     // v (indexed by node id): right-hand side in, solution out
     void solve_host(const std::vector<double> &W, const std::vector<double> &invd, std::vector<double> &v) const {
-        for (int l = 0; l < n_levels; ++l)
-            for (int c = wstep[l]; c < wstep[l + 1]; ++c) {
-                double acc = 0.0;
-                for (int q = wchunk[c]; q < wchunk[c + 1]; ++q) acc += W[fwd[q].pos] * v[fwd[q].src] * invd[fwd[q].k];
-                v[fwd[wchunk[c]].dst] -= acc;
-            }
+        auto apply = [&](int q0, int q1) {
+            double acc = 0.0;
+            for (int q = q0; q < q1; ++q) acc += W[fwd[q].pos] * v[fwd[q].src] * invd[fwd[q].k];
+            v[fwd[q0].dst] -= acc;
+        };
+        for (int l = 0; l < n_levels; ++l) {
+            for (int q = ws_beg[l]; q < ws_end[l]; ++q) apply(q, q + 1);
+            for (int c = wmstep[l]; c < wmstep[l + 1]; ++c) apply(wmchunk[c].begin, wmchunk[c].end);
+        }
         for (int k = 0; k < N; ++k) v[perm[k]] *= invd[k];
         for (int l = n_levels - 1; l >= 0; --l)
             for (int q = bstep[l]; q < bstep[l + 1]; ++q) v[bwd[q].dst] -= invd[bwd[q].k] * W[bwd[q].pos] * v[bwd[q].src];

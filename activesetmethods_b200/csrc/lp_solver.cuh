@@ -913,7 +913,7 @@ class LpSolver {
         ASM_TRY(gmax.alloc(B));
         ASM_TRY(state.alloc(B));
         ASM_TRY(prm.alloc(1));
-        ASM_TRY(n_active.alloc(1));
+        ASM_TRY(n_active.alloc(2));   // [0] running LPs, [1] barrier engine: inexact Newton steps seen
         ASM_TRY(kstep.alloc(B));
         ASM_TRY(pin_flag.reserve(64));
         host_state.resize(B);
@@ -1531,13 +1531,22 @@ class LpSolver {
         g.c0 = c0.p;
         KktDev d = E.dev();
         const Geo gr = geo_for(m, B), gc = geo_for(n, B), gm = geo_for(std::max(n, m), B), gN = geo_for((int64_t)n + m, B);
-        const int refine = P.ipm_refine >= 0 ? P.ipm_refine : 2;
+        // refinement passes per linear solve: fixed when ipm_refine >= 0, else adaptive -- one, and a second one from the
+        // moment a long Newton step fails to halve the linear residuals (k_ipm_decide counts those)
+        int refine = P.ipm_refine >= 0 ? P.ipm_refine : 1;
+        const bool adaptive = P.ipm_refine < 0;
+        g.need_refine = n_active.p + 1;
+        flag[1] = 0;
+        ASM_CK(cudaMemcpyAsync(n_active.p + 1, flag + 1, sizeof(int), cudaMemcpyHostToDevice, stream));
         const int max_it = P.ipm_max_iter > 0 ? P.ipm_max_iter : 200;
         const bool trace = getenv("ASM_TRACE") != nullptr;
         ASM_TRY(E.capture(stream, &E.g_factor, E.launches_factor, [&](int64_t &c) { E.enqueue_factor(v, stream, c); }));
         ASM_TRY(E.capture(stream, &E.g_solve_sol, E.launches_solve, [&](int64_t &c) { E.enqueue_solve(v, g.sol, stream, c); }));
         ASM_TRY(E.capture(stream, &E.g_solve_work, E.launches_solve, [&](int64_t &c) { E.enqueue_solve(v, g.work, stream, c); }));
+        E.last_pairs = 0;
+        E.last_factorisations = 0;
         auto solve_refined = [&]() -> int {
+            E.last_pairs += 1 + refine;
             ASM_CK(cudaGraphLaunch(E.g_solve_sol, stream));
             launches += E.launches_solve;
             for (int r = 0; r < refine; ++r) {
@@ -1552,15 +1561,20 @@ class LpSolver {
         ASM_KB(k_ipm_init_cols, gc, v, g);
         ASM_KB(k_ipm_init_rows, gr, v, g);
         ASM_KL(k_ipm_init_state<<<B, kFinalThreads, 0, stream>>>(v, g));
-        int it = 0;
+        int it = 0, refine_seen = 0;
         for (;; ++it) {
             ASM_KB(k_ipm_res_cols, gc, v, g);
             ASM_KB(k_ipm_res_rows, gr, v, g);
             ASM_KL(k_ipm_decide<<<B, kFinalThreads, 0, stream>>>(v, g, it, it >= max_it ? 1 : 0));
             ASM_KB(k_ipm_save, gm, v, g);
-            ASM_CK(cudaMemcpyAsync(flag, n_active.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            ASM_CK(cudaMemcpyAsync(flag, n_active.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             ASM_CK(cudaStreamSynchronize(stream));
             if (*flag <= 0 || it >= max_it) break;
+            if (adaptive && flag[1] > refine_seen && refine < 2) {
+                ++refine;
+                if (trace) fprintf(stderr, "[asm] barrier engine: step %d, %d inexact steps so far -> %d refinement pass(es)\n", it, flag[1], refine);
+            }
+            refine_seen = flag[1];
             ASM_KB(k_ipm_diag, gm, v, g, d);
             const bool timed = trace && it == 1;
             cudaEvent_t te[3] = {nullptr, nullptr, nullptr};
@@ -1570,6 +1584,7 @@ class LpSolver {
             }
             ASM_CK(cudaGraphLaunch(E.g_factor, stream));
             launches += E.launches_factor;
+            E.last_factorisations += 1;
             if (timed) cudaEventRecord(te[1], stream);
             ASM_KB2(k_ipm_rhs, false, gm, v, g);
             ASM_TRY(solve_refined());

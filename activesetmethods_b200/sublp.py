@@ -226,11 +226,11 @@ class SubLp:
 
     def ipm_info(self):
         """Sizes of the barrier engine's factorisation and the Newton steps of the last solve."""
-        st = np.zeros(8, dtype=np.int64)
+        st = np.zeros(10, dtype=np.int64)
         tm = np.zeros(4)
         capi.check(self._lib.asm_slp_ipm_info(self._h, st.ctypes.data_as(capi.c_int64_p), capi.dptr(tm)))
         keys = ("kkt_dim", "nnz_L", "terms", "levels", "factor_chunks", "forward_chunks", "launches_factor",
-                "launches_substitution")
+                "launches_substitution", "factorisations", "substitution_pairs")
         out = {k: int(v) for k, v in zip(keys, st)}
         out.update(symbolic_ms=float(tm[0]), newton_steps=int(tm[1]))
         return out

@@ -353,7 +353,7 @@ def run_ours(a):
         resident_step()
     e2e_step()
     eng = lp.engine_info()
-    kst = lp.ipm_info() if eng["engine"] == 4 else None
+    kst = lp.ipm_info() if eng["engine"] == 4 else None      # sizes; the per-solve counters are refreshed below
     # timing rule: inputs larger than L2, or flush L2 between timed steps (outside the timed region)
     Bpad = 1 if S <= 1 else (32 if S <= 32 else ((S + 63) // 64) * 64)
     working_set = Bpad * (8 * (kst["nnz_L"] + 2 * kst["kkt_dim"]) if kst else (16 * nnz_csr + 64 * n + 48 * m))
@@ -411,6 +411,7 @@ def run_ours(a):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if kst is not None:
+        kst = lp.ipm_info()
         fac_ms, pair_ms = lp.ipm_timing(10)
         by_fac, by_pair = kkt_bytes(kst, Bpad)
         newton = its_sum / total_scen
@@ -429,8 +430,8 @@ def run_ours(a):
                     "substitution_pair_ms": pair_ms, "substitution_pair_bytes": by_pair,
                     "substitution_pair_gbs": by_pair / (pair_ms * 1e-3) / 1e9,
                     "newton_steps_mean": newton, "kkt": kst,
-                    "share_of_step": {"factor": newton * fac_ms / (1e3 * dev_s / a.steps),
-                                      "substitutions": newton * 2 * (1 + lp.params.ipm_refine) * pair_ms / (1e3 * dev_s / a.steps)}}
+                    "share_of_step": {"factor": kst["factorisations"] * fac_ms / (1e3 * dev_s / a.steps),
+                                      "substitutions": kst["substitution_pairs"] * pair_ms / (1e3 * dev_s / a.steps)}}
     else:
         pm, dm = lp.kernel_timing(50)
         by_primal = Bpad * (8 * nnz_csr + 8 * m + 56 * n) + 4 * nnz_csr + 4 * (n + 1)

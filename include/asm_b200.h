@@ -78,7 +78,8 @@ typedef struct asm_lp_params {
                            /* empty by the equilibration (0 = default 1e-8)                                            */
     /* barrier engine (engine 0 / 4) */
     int32_t ipm_max_iter;  /* Newton steps per LP (default 200)                                                        */
-    int32_t ipm_refine;    /* iterative-refinement passes per linear solve (default 2)                                 */
+    int32_t ipm_refine;    /* iterative-refinement passes per linear solve (default 1); -1: one, and a second one from */
+                           /* the moment a long Newton step fails to halve the linear residuals                        */
     double ipm_reg;        /* static regularisation d of the quasi-definite system (default 1e-8, scaled units)        */
     double ipm_prox;       /* least-norm selection: proximal weight q = ipm_prox (1 + |c|) / (2 max(1, |x|)), i.e. the */
                            /* relative dual residual it may leave in the LP (default 1e-7; 0 = pure LP)                */
@@ -243,8 +244,9 @@ int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations);
  * whether the matrix values stay resident there, and the padded entry count of the row side */
 int asm_plan_check(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, int32_t G,
                    int64_t *smem_bytes, int32_t *matrix_resident, int64_t *padded_entries);
-/* barrier engine (engine 0 / 4) instrumentation.  stats[8]: KKT dimension, nnz(L), update terms, levels, factor chunks,
- * forward-substitution chunks, kernel launches per factorisation, per substitution pair; times[4]: symbolic analysis
+/* barrier engine (engine 0 / 4) instrumentation.  stats[10]: KKT dimension, nnz(L), update terms, levels, factor chunks,
+ * forward-substitution chunks, kernel launches per factorisation, per substitution pair, factorisations and substitution
+ * pairs of the last solve; times[4]: symbolic analysis
  * ms, Newton steps of the last solve, factor / solve ms of the traced step (ASM_TRACE=1).  Either pointer may be NULL */
 int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times);
 /* average device time (CUDA events on the handle's stream) of one numeric factorisation and one substitution pair of
