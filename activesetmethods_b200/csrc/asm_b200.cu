@@ -507,8 +507,11 @@ struct SlpHandle {
     DBuf<double> xL, xU, gL, gU, xk, df, E, dE, fval, delta, d_alpha;
     DBuf<double> p, lam, muU, muL, pslack, tmp_m, tmp_m2, tmp_n, tmp_n2, tmp_n3, small_out, partials;
     DBuf<int> d_status;
-    DBuf<double> stage;  // device staging for layout changes
+    DBuf<double> stage;
+    // device staging for layout changes
+    PinnedRing ring;   // host -> device copies of pageable caller arrays (see util.cuh)
     std::unique_ptr<LpSolver> normal, fr;
+    std::vector<int32_t> mask;   // asm_slp_set_active (kept for the restoration solver, which is built lazily)
     int phase = -1;  // phase of the last update
     bool solved = false, extracted = false;
     Pinned pin_small;
@@ -555,12 +558,12 @@ struct SlpHandle {
     // host [S][len] -> device [len][B]
     int put(const double *host, int64_t len, int S, double *dst) {
         if (len == 0) return ASM_OK;
-        if (B == 1) {
-            ASM_CK(cudaMemcpyAsync(dst, host, len * sizeof(double), cudaMemcpyHostToDevice, stream));
-            return ASM_OK;
+        if (B == 1) return ring.h2d(dst, host, len * sizeof(double), stream);
+        if (stage.n < (size_t)len * S) {
+            ASM_CK(cudaStreamSynchronize(stream));   // earlier layout kernels may still read the old buffer
+            ASM_TRY(stage.alloc((size_t)len * S));
         }
-        if (stage.n < (size_t)len * S) ASM_TRY(stage.alloc((size_t)len * S));
-        ASM_CK(cudaMemcpyAsync(stage.p, host, (size_t)len * S * sizeof(double), cudaMemcpyHostToDevice, stream));
+        ASM_TRY(ring.h2d(stage.p, host, (size_t)len * S * sizeof(double), stream));
         dim3 grid((unsigned)((len + 31) / 32), B / 32), block(32, 8);
         k_layout_in<<<grid, block, 0, stream>>>(stage.p, dst, len, S, B);
         ++own_launches;
@@ -573,13 +576,16 @@ struct SlpHandle {
             ASM_CK(cudaMemcpyAsync(host, src, len * sizeof(double), cudaMemcpyDeviceToHost, stream));
             return ASM_OK;
         }
-        if (stage.n < (size_t)len * Buser) ASM_TRY(stage.alloc((size_t)len * Buser));
+        if (stage.n < (size_t)len * Buser) {
+            ASM_CK(cudaStreamSynchronize(stream));   // earlier copies may still read the old buffer
+            ASM_TRY(stage.alloc((size_t)len * Buser));
+        }
         dim3 grid((unsigned)((len + 31) / 32), B / 32), block(32, 8);
         k_layout_out<<<grid, block, 0, stream>>>(src, stage.p, len, Buser, B);
         ++own_launches;
+        // stream order protects the staging buffer (the next get()'s kernel runs after this copy); the caller of get()
+        // synchronises ONCE, after its last array
         ASM_CK(cudaMemcpyAsync(host, stage.p, (size_t)len * Buser * sizeof(double), cudaMemcpyDeviceToHost, stream));
-        // the staging buffer is reused by the next get(): wait for this copy
-        ASM_CK(cudaStreamSynchronize(stream));
         return ASM_OK;
     }
 
@@ -729,6 +735,7 @@ struct SlpHandle {
         nnz_fr = (int64_t)ci.size();
         fr.reset(new LpSolver());
         ASM_TRY(fr->init(ncol_fr, nrow_fr, nnz_fr, rp.data(), ci.data(), Buser, stream));
+        if (!mask.empty()) ASM_TRY(fr->set_active(mask.data()));
         ASM_TRY(fr_src.alloc(src.size()));
         ASM_CK(cudaMemcpy(fr_src.p, src.data(), src.size() * sizeof(int), cudaMemcpyHostToDevice));
         return ASM_OK;
@@ -868,14 +875,12 @@ struct asm_lp {
     int device = 0;
     explicit asm_lp(bool partitioned) : dist(partitioned ? new DistLp() : nullptr), s(partitioned ? dist->lp : own) {}
     DBuf<double> stage;
+    PinnedRing ring;
     int put(const double *host, int64_t len, int S, double *dst) {
         if (len == 0) return ASM_OK;
-        if (s.B == 1) {
-            ASM_CK(cudaMemcpyAsync(dst, host, len * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-            return ASM_OK;
-        }
+        if (s.B == 1) return ring.h2d(dst, host, len * sizeof(double), s.stream);
         if (stage.n < (size_t)len * S) ASM_TRY(stage.alloc((size_t)len * S));
-        ASM_CK(cudaMemcpyAsync(stage.p, host, (size_t)len * S * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        ASM_TRY(ring.h2d(stage.p, host, (size_t)len * S * sizeof(double), s.stream));
         dim3 grid((unsigned)((len + 31) / 32), s.B / 32), block(32, 8);
         k_layout_in<<<grid, block, 0, s.stream>>>(stage.p, dst, len, S, s.B);
         ASM_CK(cudaStreamSynchronize(s.stream));
@@ -1111,6 +1116,17 @@ int asm_slp_solve(asm_slp *h, const asm_lp_params *params, asm_lp_info *info) {
     if (!h) return fail(ASM_E_INVALID, "null handle");
     return h->h.solve(params, info);
 }
+int asm_slp_set_active(asm_slp *h, const int32_t *active) {
+    if (!h) return fail(ASM_E_INVALID, "null handle");
+    ASM_CK(cudaSetDevice(h->h.device));
+    ASM_TRY(h->h.normal->set_active(active));
+    if (h->h.fr) ASM_TRY(h->h.fr->set_active(active));
+    if (active)
+        h->h.mask.assign(active, active + h->h.Buser);
+    else
+        h->h.mask.clear();
+    return ASM_OK;
+}
 int asm_slp_extract(asm_slp *h, double *p, double *lambda, double *mult_x_U, double *mult_x_L, double *p_slack,
                     int32_t *status) {
     if (!h) return fail(ASM_E_INVALID, "null handle");
@@ -1272,6 +1288,11 @@ int asm_slp_attach_acopf(asm_slp *hh, const asm_acopf_desc *d) {
     if (!d->f_bus || !d->t_bus || !d->coef || !d->gs || !d->bs || !d->cost2 || !d->cost1 || !d->cost0 || !d->bal_ptr ||
         (d->nd > 0 && !d->dc_loss1))
         return fail(ASM_E_INVALID, "null array in the ACOPF description");
+    if (d->bal_ptr[0] != 0) return fail(ASM_E_INVALID, "bal_ptr must start at 0");
+    for (int i = 0; i < 2 * d->nb; ++i)
+        if (d->bal_ptr[i + 1] < d->bal_ptr[i]) return fail(ASM_E_INVALID, "bal_ptr is not monotone");
+    if (d->bal_ptr[2 * d->nb] > 0 && (!d->bal_col || !d->bal_coef))
+        return fail(ASM_E_INVALID, "null balance-row lists in the ACOPF description");
     AcopfDev a;
     a.nb = d->nb; a.ng = d->ng; a.nl = d->nl; a.nd = d->nd; a.ref_bus = d->ref_bus;
     a.nnz_bal = d->bal_ptr[2 * d->nb];
@@ -1570,9 +1591,9 @@ int asm_slp_kernel_timing(asm_slp *h, int32_t reps, double *primal_ms, double *d
     return h->h.cur()->time_streaming_kernels(reps, primal_ms, dual_ms);
 }
 
-// sizes of the barrier engine's factorisation (stats[10]: KKT dimension, nnz(L), update terms, levels, factor chunks,
+// sizes of the barrier engine's factorisation (stats[14]: KKT dimension, nnz(L), update terms, levels, factor chunks,
 // forward chunks, launches per factorisation, launches per substitution pair, factorisations and substitution pairs of
-// the last solve) and (times[4]) symbolic analysis ms,
+// the last solve, distinct operand reads / targets per factorisation, per substitution pair, summed over the levels) and (times[4]) symbolic analysis ms,
 // Newton steps of the last solve, factor / solve ms of the traced step (ASM_TRACE)
 int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times) {
     if (!h) return fail(ASM_E_INVALID, "null handle");
@@ -1590,6 +1611,10 @@ int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times) {
         stats[7] = E.launches_solve;
         stats[8] = E.last_factorisations;
         stats[9] = E.last_pairs;
+        stats[10] = E.sym.f_distinct_reads;
+        stats[11] = E.sym.f_targets;
+        stats[12] = E.sym.w_distinct_reads + E.sym.b_distinct_reads;
+        stats[13] = E.sym.w_targets + E.sym.b_targets;
     }
     if (times) {
         times[0] = E.symbolic_ms;

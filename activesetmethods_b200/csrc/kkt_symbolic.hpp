@@ -69,6 +69,9 @@ struct KktSymbolic {
     std::vector<int> fs_beg, fs_end, fmstep;
     std::vector<KktRange> fmchunk;
     int64_t n_fchunks = 0, n_wchunks = 0;
+    // distinct f64 operands a step has to read / targets it has to read and write, summed over the steps: the traffic a
+    // batch whose working set exceeds L2 cannot avoid (nothing survives in cache from one level to the next)
+    int64_t f_distinct_reads = 0, f_targets = 0, w_distinct_reads = 0, w_targets = 0, b_distinct_reads = 0, b_targets = 0;
     int longest_chunk = 0;
     // forward substitution, same layout
     std::vector<KktFwdItem> fwd;
@@ -264,6 +267,38 @@ struct KktSymbolic {
             for (int l = 0; l < n_levels; ++l) w[l + 1] = w[l] + (se[l] - sb[l]) + (ms[l + 1] - ms[l]);
             return w;
         };
+        {   // compulsory traffic per step (see f_distinct_reads)
+            std::vector<int> stampW(nnzL + 1, -1), stampD(N, -1), stampV(N, -1), stampT(nnzL + N + 1, -1);
+            size_t q = 0;
+            for (int l = 0; l < n_levels; ++l)
+                for (; q < terms.size() && level[terms[q].k] == l; ++q) {
+                    const KktTerm &u = terms[q];
+                    const int t = u.t & ~kLastBit;
+                    if (stampW[u.a] != l) { stampW[u.a] = l; ++f_distinct_reads; }
+                    if (stampW[u.b] != l) { stampW[u.b] = l; ++f_distinct_reads; }
+                    if (stampD[u.k] != l) { stampD[u.k] = l; ++f_distinct_reads; }
+                    if (stampT[t] != l) { stampT[t] = l; ++f_targets; }
+                }
+            std::fill(stampD.begin(), stampD.end(), -1);
+            std::vector<int> stampDst(N, -1);
+            q = 0;
+            for (int l = 0; l < n_levels; ++l)
+                for (; q < fwd.size() && level[fwd[q].k] == l; ++q) {
+                    const KktFwdItem &u = fwd[q];
+                    ++w_distinct_reads;                                   // W[pos]: every entry of L exactly once
+                    if (stampV[u.src] != l) { stampV[u.src] = l; w_distinct_reads += 2; }   // v[src], 1/d[k]
+                    if (stampDst[u.dst] != l) { stampDst[u.dst] = l; ++w_targets; }
+                }
+            std::fill(stampV.begin(), stampV.end(), -1);
+            std::fill(stampDst.begin(), stampDst.end(), -1);
+            for (int l = 0; l < n_levels; ++l)
+                for (int p = bstep[l]; p < bstep[l + 1]; ++p) {
+                    const KktBwdItem &u = bwd[p];
+                    ++b_distinct_reads;
+                    if (stampV[u.src] != l) { stampV[u.src] = l; ++b_distinct_reads; }
+                    if (stampDst[u.dst] != l) { stampDst[u.dst] = l; b_distinct_reads += 1; ++b_targets; }   // 1/d[dst]
+                }
+        }
         plan(work(fs_beg, fs_end, fmstep), narrow, flaunch);
         plan(work(ws_beg, ws_end, wmstep), narrow, wlaunch);
         plan(bstep, narrow, blaunch);

@@ -706,6 +706,16 @@ __global__ void k_mark_padding(ScenState *st, int Buser, int B) {
     if (s < B) st[s].status = ASM_LP_OPTIMAL;
 }
 
+// scenarios masked out of this solve (asm_slp_set_active): never live
+__global__ void k_apply_mask(ScenState *st, const int *active, int Buser) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < Buser && !active[s]) {
+        st[s].status = ASM_LP_SKIPPED;
+        st[s].total = 0;
+        st[s].pobj = st[s].dobj = st[s].pres = st[s].dres = st[s].gap = 0.0;
+    }
+}
+
 // unscale the final iterate; bound duals from the reduced costs of the last check
 template <bool BATCH>
 __global__ void __launch_bounds__(kThreads) k_finalize(LpView v) {
@@ -796,6 +806,7 @@ class LpSolver {
     int64_t nnz = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    int device = 0;   // the device this handle lives on (current at init)
     // pattern
     DBuf<int> row_ptr, col_idx, col_ptr, row_idx, csc_src;
     std::vector<int> h_row_ptr, h_col_idx, h_col_ptr, h_row_idx, h_csc_src;
@@ -816,6 +827,8 @@ class LpSolver {
     int homeB = 0, homeBuser = 0;
     int compactions = 0;
     int last_engine = 0, last_G = 0, last_groups = 0;
+    DBuf<int> d_active;               // asm_slp_set_active: mask of the scenarios the next solves work on
+    int n_masked = -1;                // number of active scenarios of the mask; -1 = no mask
     std::unique_ptr<IpmEngine> ipm;   // barrier engine (ipm.cuh), built at the first solve that uses it
     int ipm_failed = 0;               // symbolic analysis refused this pattern: engine 0 stays on PDHG
     // data (unscaled, element-major)
@@ -852,6 +865,7 @@ class LpSolver {
         Buser = batch;
         B = pad_batch(batch);
         if (n <= 0 || m < 0 || nnz < 0 || batch < 1) return fail(ASM_E_INVALID, "bad LP dimensions");
+        ASM_CK(cudaGetDevice(&device));
         if (nnz > 0x7fffffffLL) return fail(ASM_E_INVALID, "nnz exceeds 2^31-1");
         if (rp64[0] != 0 || rp64[m] != nnz) return fail(ASM_E_INVALID, "row_ptr does not match nnz");
         if (st) {
@@ -1511,6 +1525,20 @@ class LpSolver {
         return ASM_OK;
     }
 
+    int set_active(const int32_t *active) {
+        if (!active) {
+            n_masked = -1;
+            return ASM_OK;
+        }
+        if (d_active.n < (size_t)Buser) ASM_TRY(d_active.alloc(Buser));
+        std::vector<int> h(active, active + Buser);
+        n_masked = 0;
+        for (int v : h) n_masked += v != 0;
+        ASM_CK(cudaMemcpyAsync(d_active.p, h.data(), sizeof(int) * Buser, cudaMemcpyHostToDevice, stream));
+        ASM_CK(cudaStreamSynchronize(stream));
+        return ASM_OK;
+    }
+
     // ---- barrier engine: Mehrotra predictor-corrector on the fixed-pattern L D L' (ipm.cuh) ----------------------
     int ensure_ipm() {
         if (ipm) return ASM_OK;
@@ -1747,6 +1775,12 @@ class LpSolver {
             use_ipm = false;
         }
         ASM_TRY(precondition(P.ruiz_iters, (!use_ipm && P.warm_start && has_solution) ? (int)P.warm_start : 0));
+        if (n_masked >= 0) {
+            ASM_KL(k_apply_mask<<<(Buser + 127) / 128, 128, 0, stream>>>(state.p, d_active.p, Buser));
+            *flag = n_masked;
+            ASM_CK(cudaMemcpyAsync(n_active.p, flag, sizeof(int), cudaMemcpyHostToDevice, stream));
+            ASM_CK(cudaStreamSynchronize(stream));
+        }
         const int steps = std::max(2, (int)P.check_every);
         // engine 1: streaming kernels only (one launch per half iteration, CUDA graph per check period);
         // engine 2: persistent group kernel only;
@@ -1765,7 +1799,7 @@ class LpSolver {
         last_engine = 0;
         last_G = 0;
         last_groups = 0;
-        int live = Buser;
+        int live = n_masked >= 0 ? n_masked : Buser;
         bool limit = false;
         const bool trace = getenv("ASM_TRACE") != nullptr;
         auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1778,7 +1812,7 @@ class LpSolver {
             // kernels move the whole working set at ~4.4 TB/s plus two launches; the group kernel costs
             // (sync + work / G) on G of the machine's SMs
             int n_sms = kSMs;
-            cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, 0);
+            cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
             const double bytes_it = 16.0 * (double)nnz + 64.0 * n + 48.0 * m;
             auto stream_cost = [&](int Bc, int lv) { return ((double)Bc * bytes_it / 4.4e12 + 8e-6) / std::max(1, lv); };
             auto group_cost = [&](int lv) {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -81,6 +82,51 @@ struct Pinned {
         bytes = 0;
         ASM_CK(cudaHostAlloc(&p, b, cudaHostAllocDefault));
         bytes = b;
+        return ASM_OK;
+    }
+};
+
+// Host -> device copies of caller-owned arrays.  A Julia Vector{Float64} (or a numpy array) is pageable memory: an
+// async copy from it is staged by the driver and is not asynchronous at all.  When the caller's pointer is pinned
+// (cudaHostRegister / cudaHostAlloc) the copy goes straight from it; otherwise it goes through this handle's own ring
+// of two pinned chunks, the memcpy into one chunk overlapping the DMA out of the other.
+struct PinnedRing {
+    static constexpr size_t kChunk = 8u << 20;
+    Pinned buf[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    int next = 0;
+    ~PinnedRing() {
+        for (auto &e : ev)
+            if (e) cudaEventDestroy(e);
+    }
+    static bool is_pinned(const void *p) {
+        cudaPointerAttributes at;
+        const cudaError_t e = cudaPointerGetAttributes(&at, p);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+    }
+    int h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+        if (bytes == 0) return ASM_OK;
+        if (is_pinned(src)) {
+            ASM_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+            return ASM_OK;
+        }
+        for (size_t off = 0; off < bytes; off += kChunk) {
+            const size_t sz = std::min(kChunk, bytes - off);
+            const int i = next;
+            next ^= 1;
+            ASM_TRY(buf[i].reserve(kChunk));
+            if (!ev[i]) ASM_CK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            if (used[i]) ASM_CK(cudaEventSynchronize(ev[i]));   // the DMA out of this chunk has finished
+            memcpy(buf[i].p, (const char *)src + off, sz);
+            ASM_CK(cudaMemcpyAsync((char *)dst + off, buf[i].p, sz, cudaMemcpyHostToDevice, st));
+            ASM_CK(cudaEventRecord(ev[i], st));
+            used[i] = true;
+        }
         return ASM_OK;
     }
 };

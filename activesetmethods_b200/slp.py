@@ -312,6 +312,10 @@ class SlpLS(_Slp):
             self.compl = self.norm_complementarity()
             self.p, self.lam, self.mult_x_U, self.mult_x_L, self.p_slack, status = self.sub_optimize(1000.0, True)
             if status not in (LP_OPTIMAL, LP_INFEASIBLE):
+                # Deviation from slp_line_search.jl:129, whose `slp.ret == -3` is a comparison, not an assignment: the
+                # run would end as -5 "Optimize_not_called" after a full solve.  -3 (Error_In_Step_Computation) is the
+                # evident intent.
+                self.ret = -3
                 if self.prim_infeas <= o.tol_infeas:
                     self.ret = 6
                 break
@@ -409,6 +413,7 @@ class SlpTR(_Slp):
             self.eval_functions()
             self.p, self.lam, self.mult_x_U, self.mult_x_L, self.p_slack, status = self.sub_optimize(self.delta)
             if status not in (LP_OPTIMAL, LP_INFEASIBLE):
+                self.ret = -3                      # same deviation as in SlpLS.run (slp_trust_region.jl:131)
                 if self.optimizer.norm_violations(pr.eval_g(self.x, np.zeros(pr.m)), self.x, 1) <= o.tol_infeas:
                     self.ret = 6
                 break
@@ -509,6 +514,16 @@ class SlpLSBatch:
                         device=o.device, **{"warm_start": 1, **o.lp_options})
             opt._squeeze = False
             if self.device_evaluator:
+                # the device evaluator holds ONE network: every scenario must share everything but its loads (which
+                # only enter g_L / g_U)
+                n0 = prs[0].net
+                for k, pr in enumerate(prs[1:], 1):
+                    for name in ("f_bus", "t_bus", "br_r", "br_x", "br_b", "tap", "shift", "gs", "bs", "cost2", "cost1",
+                                 "cost0", "gen_bus", "dc_loss1"):
+                        if not np.array_equal(getattr(pr.net, name), getattr(n0, name)):
+                            raise ValueError(f"device_evaluator: scenario {k} differs from scenario 0 in network.{name}")
+                    if pr.net.ref_bus != n0.ref_bus:
+                        raise ValueError(f"device_evaluator: scenario {k} has another reference bus")
                 opt.attach_acopf(prs[0])
             return opt
         if self.device_evaluator:
@@ -523,10 +538,14 @@ class SlpLSBatch:
         pr.eval_g(self.x[s], self.E[s])
         pr.eval_jac_g(self.x[s], "eval", None, None, self.dE[s])
 
-    def _solve_phase(self, fr):
+    def _solve_phase(self, fr, sel=None):
         """Sub-LP batch of one phase; returns the extract tuple plus phi(0) and the directional derivative computed
-        while the device still holds this phase's step and slacks."""
+        while the device still holds this phase's step and slacks.  ``sel``: the scenarios that are running in this
+        phase -- the others (terminated, or in the other phase, whose normal LP is infeasible by construction) are
+        masked out of the solve instead of being re-solved every round."""
         opt = self.optimizer
+        if sel is not None and hasattr(opt, "set_active"):
+            opt.set_active(sel)
         if fr and self.device_evaluator:
             opt.eval_acopf(self.x, 1000.0, True)
         elif fr:                    # the normal-phase data push was done for the KKT metrics of this round
@@ -569,7 +588,7 @@ class SlpLSBatch:
                 sel = need[fr]
                 if not sel.any():
                     continue
-                p, lam, mu_u, mu_l, slack, st = self._solve_phase(fr)
+                p, lam, mu_u, mu_l, slack, st = self._solve_phase(fr, sel)
                 idx = np.nonzero(sel)[0]
                 self.p[idx], self.lam[idx], self.mult_x_U[idx], self.mult_x_L[idx] = p[idx], lam[idx], mu_u[idx], mu_l[idx]
                 status[idx] = st[idx]
@@ -587,8 +606,7 @@ class SlpLSBatch:
             for s in run:
                 st = status[s]
                 if st not in (LP_OPTIMAL, LP_INFEASIBLE):
-                    if self.prim_infeas[s] <= o.tol_infeas:
-                        self.ret[s] = 6
+                    self.ret[s] = 6 if self.prim_infeas[s] <= o.tol_infeas else -3   # see SlpLS.run
                     self.running[s] = False
                     continue
                 if st == LP_INFEASIBLE:

@@ -102,6 +102,16 @@ class SubLp:
             capi.dptr(self._vec(E, self.m)), capi.dptr(self._vec(dE, self.nnz_coo)), capi.dptr(self._scal(delta)),
             1 if feasibility else 0))
 
+    def set_active(self, mask=None):
+        """Restrict the following solves to the scenarios with ``mask[s]`` true (``None``: all again).  Masked
+        scenarios come back with status ``LP_SKIPPED`` (5) and zeroed outputs."""
+        if mask is None:
+            capi.check(self._lib.asm_slp_set_active(self._h, None))
+            return
+        m = np.ascontiguousarray(np.asarray(mask).astype(bool), dtype=np.int32)
+        assert m.shape == (self.batch,)
+        capi.check(self._lib.asm_slp_set_active(self._h, m.ctypes.data_as(capi.c_int32_p)))
+
     def solve(self):
         info = (capi.LpInfo * self.batch)()
         capi.check(self._lib.asm_slp_solve(self._h, C.byref(self.params), info))
@@ -226,11 +236,12 @@ class SubLp:
 
     def ipm_info(self):
         """Sizes of the barrier engine's factorisation and the Newton steps of the last solve."""
-        st = np.zeros(10, dtype=np.int64)
+        st = np.zeros(14, dtype=np.int64)
         tm = np.zeros(4)
         capi.check(self._lib.asm_slp_ipm_info(self._h, st.ctypes.data_as(capi.c_int64_p), capi.dptr(tm)))
         keys = ("kkt_dim", "nnz_L", "terms", "levels", "factor_chunks", "forward_chunks", "launches_factor",
-                "launches_substitution", "factorisations", "substitution_pairs")
+                "launches_substitution", "factorisations", "substitution_pairs", "factor_distinct_reads",
+                "factor_targets", "substitution_distinct_reads", "substitution_targets")
         out = {k: int(v) for k, v in zip(keys, st)}
         out.update(symbolic_ms=float(tm[0]), newton_steps=int(tm[1]))
         return out

@@ -211,15 +211,18 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------------------
 def kkt_bytes(st, B):
     """Algorithmic bytes of one numeric factorisation and of one substitution pair of a batch of B LPs (DESIGN.md
-    section 4.4): f64 operands the fan-out schedule has to move per scenario, plus the index lists, which a warp reads
-    once for its 32 scenarios."""
-    terms, fch, wch, nnzL, N = st["terms"], st["factor_chunks"], st["forward_chunks"], st["nnz_L"], st["kkt_dim"]
-    per_lp_factor = 24 * terms + 16 * fch + 8 * nnzL + 16 * N        # W[a], W[b], 1/d[k]; target read+write; clear; pivots
-    idx_factor = 16 * terms + 4 * fch
-    per_lp_pair = (24 * nnzL + 16 * wch) + 24 * N + 40 * nnzL        # forward items + targets; diagonal pass; backward
-    idx_pair = 16 * nnzL + 4 * wch + 16 * nnzL
+    section 4.4).  A level's kernel must read every distinct f64 operand it uses once and read + write every target once;
+    nothing survives in L2 from one level to the next when the batch working set (nnz(L) * B * 8 bytes) is much larger
+    than L2.  Index lists are read once per warp, i.e. once per 32 scenarios.  Operands that several chunks of one
+    level share are counted once -- the kernel re-reads them (from L1 / L2), so this is a lower bound of what it moves
+    and `achieved` is conservative."""
+    fr, ft = st["factor_distinct_reads"], st["factor_targets"]
+    sr, stg = st["substitution_distinct_reads"], st["substitution_targets"]
+    nnzL, N, terms = st["nnz_L"], st["kkt_dim"], st["terms"]
+    per_lp_factor = 8 * fr + 16 * ft + 8 * nnzL + 8 * nnzL // 2 + 16 * N   # + clear W, scatter K, pivots in / out
+    per_lp_pair = 8 * sr + 16 * stg + 24 * N                                # + the diagonal pass
     warps = max(1, B // 32)
-    return B * per_lp_factor + warps * idx_factor, B * per_lp_pair + warps * idx_pair
+    return B * per_lp_factor + warps * 16 * terms, B * per_lp_pair + warps * 32 * nnzL
 
 
 def single_instance(a, local):

@@ -45,6 +45,7 @@ extern "C" {
 #define ASM_LP_DUAL_INFEASIBLE 2
 #define ASM_LP_ITERATION_LIMIT 3
 #define ASM_LP_NUMERICAL_ERROR 4
+#define ASM_LP_SKIPPED 5 /* the scenario was masked out of this solve (asm_slp_set_active) */
 
 const char *asm_last_error(void);
 /* number of visible CUDA devices (0 if none); never fails */
@@ -244,9 +245,10 @@ int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations);
  * whether the matrix values stay resident there, and the padded entry count of the row side */
 int asm_plan_check(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, int32_t G,
                    int64_t *smem_bytes, int32_t *matrix_resident, int64_t *padded_entries);
-/* barrier engine (engine 0 / 4) instrumentation.  stats[10]: KKT dimension, nnz(L), update terms, levels, factor chunks,
+/* barrier engine (engine 0 / 4) instrumentation.  stats[14]: KKT dimension, nnz(L), update terms, levels, factor chunks,
  * forward-substitution chunks, kernel launches per factorisation, per substitution pair, factorisations and substitution
- * pairs of the last solve; times[4]: symbolic analysis
+ * pairs of the last solve, distinct f64 operands read / targets updated per factorisation and per substitution pair
+ * (summed over the levels: the compulsory HBM traffic of a batch larger than L2); times[4]: symbolic analysis
  * ms, Newton steps of the last solve, factor / solve ms of the traced step (ASM_TRACE=1).  Either pointer may be NULL */
 int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times);
 /* average device time (CUDA events on the handle's stream) of one numeric factorisation and one substitution pair of
@@ -258,6 +260,11 @@ int asm_slp_ipm_timing(asm_slp *h, int32_t reps, double *factor_ms, double *solv
  * factor / forward / backward launches, longest chunk, chunks */
 int asm_kkt_selftest(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, const double *vals,
                      const double *dx, const double *ew, double *rhs_sol, int64_t *stats);
+
+/* Restrict the following solves of a batch to the scenarios with active[s] != 0 (active[batch]; NULL = all again).
+ * A lock-step batch of SLP runs calls this every round: scenarios that have terminated, or that are in the other
+ * phase, cost nothing and come back with status ASM_LP_SKIPPED and zeroed outputs. */
+int asm_slp_set_active(asm_slp *h, const int32_t *active);
 
 /* which engine the last asm_slp_solve used (1 streaming, 2 group, 3 both, 4 barrier), blocks per LP and LPs resident at once */
 int asm_slp_engine_info(asm_slp *h, int32_t *engine, int32_t *group_size, int32_t *groups);

@@ -479,6 +479,7 @@ class SlpLS(_Slp):
             self.compl = self.norm_complementarity()
             self.p, self.lam, self.mult_x_U, self.mult_x_L, self.p_slack, status = self.sub_optimize()
             if status not in (OPTIMAL, INFEASIBLE):
+                self.ret = -3          # :129 compares (`slp.ret == -3`) where it means to assign; see DESIGN.md
                 if self.prim_infeas <= o.tol_infeas:
                     self.ret = 6
                 break
@@ -575,6 +576,7 @@ class SlpTR(_Slp):
             self.p, self.lam, self.mult_x_U, self.mult_x_L, self.p_slack, status = self.sub_optimize(self.delta)
             if status not in (OPTIMAL, INFEASIBLE):
                 # norm_violations(slp, slp.x): 1-norm, bound part on slp.x (App. C-8)
+                self.ret = -3
                 if norm_violations(pr.eval_g(self.x, np.zeros(pr.m)), pr.g_L, pr.g_U, self.x, pr.x_L, pr.x_U, 1) \
                         <= o.tol_infeas:
                     self.ret = 6
