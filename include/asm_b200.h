@@ -168,7 +168,9 @@ int asm_slp_get_csr(asm_slp *h, int32_t s, int64_t *row_ptr, int32_t *col_idx, d
 /* eval_functions! hand-over (slp.jl:186-191) + the data push of sub_optimize! (subproblem.jl:248-484):
  * x_k[batch][n], f[batch], df[batch][n], E[batch][m], dE[batch][nnz_coo] (j_str order), delta[batch],
  * feasibility (shared flag: 0 normal phase, 1 feasibility restoration).
- * Copies through pinned staging, assembles the CSR, builds column / row / slack bounds on the device. */
+ * Host -> device: straight from the caller's arrays when they are pinned (cudaHostRegister / cudaHostAlloc), else
+ * through the handle's own ring of two pinned 8 MB chunks (memcpy overlapping the DMA); then the CSR is assembled and
+ * the column / row / slack bounds are built on the device. */
 int asm_slp_update(asm_slp *h, const double *x_k, const double *f, const double *df, const double *E,
                    const double *dE, const double *delta, int32_t feasibility);
 /* MOI.optimize! on the current sub-LP (subproblem.jl:490); device-resident, no host copies except the
