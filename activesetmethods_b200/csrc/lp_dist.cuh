@@ -281,7 +281,7 @@ class DistLp {
         ASM_KL(k_reduce_prep<<<1, kFinalThreads, 0, stream>>>(v, rank, psum.p));
         ASM_TRY(allreduce(psum.p, psum.p, 4, NcclApi::kSum));
         ASM_KL(k_init_state_q<<<1, 1, 0, stream>>>(v, psum.p));
-        ASM_KL(k_prepare_finish<false><<<gm.grid, gm.block, 0, stream>>>(v, warm));
+        ASM_KL(k_prepare_finish<false><<<gm.grid, gm.block, 0, stream>>>(v, warm, (const int *)nullptr));
         ASM_CK(cudaGetLastError());
         return ASM_OK;
     }

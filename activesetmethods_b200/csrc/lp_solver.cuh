@@ -247,9 +247,12 @@ __global__ void __launch_bounds__(kFinalThreads) k_init_state(LpView v) {
 }
 // second pass: bound/objective rescaling and the starting point (x0, y0 are unscaled warm starts or 0)
 template <bool BATCH>
-__global__ void __launch_bounds__(kThreads) k_prepare_finish(LpView v, int warm) {
+__global__ void __launch_bounds__(kThreads) k_prepare_finish(LpView v, int warm_all, const int *__restrict__ prev_ok) {
     Map<BATCH> mp;
     const int B = v.B;
+    // a scenario is warm-started only from an OPTIMAL previous solve: after INFEASIBLE the stored duals are a growing
+    // Farkas direction, after an iteration limit an unconverged point
+    const int warm = (warm_all && (!prev_ok || prev_ok[mp.s])) ? warm_all : 0;
     const double sb = v.state[mp.s].sb, sc = v.state[mp.s].sc;
     for (int64_t j = mp.first; j < v.n; j += mp.stride) {
         const int64_t e = j * B + mp.s;
@@ -827,6 +830,7 @@ class LpSolver {
     int homeB = 0, homeBuser = 0;
     int compactions = 0;
     int last_engine = 0, last_G = 0, last_groups = 0;
+    DBuf<int> d_prev_ok;              // per scenario: the previous solve ended OPTIMAL (gates the PDHG warm start)
     DBuf<int> d_active;               // asm_slp_set_active: mask of the scenarios the next solves work on
     int n_masked = -1;                // number of active scenarios of the mask; -1 = no mask
     std::unique_ptr<IpmEngine> ipm;   // barrier engine (ipm.cuh), built at the first solve that uses it
@@ -1119,7 +1123,7 @@ class LpSolver {
         ASM_KB(k_prepare_cols, gc, v);
         ASM_KB(k_prepare_rows, gr, v);
         ASM_KL(k_init_state<<<B, kFinalThreads, 0, stream>>>(v));
-        ASM_KB(k_prepare_finish, gm, v, warm);
+        ASM_KB(k_prepare_finish, gm, v, warm, (const int *)(warm ? d_prev_ok.p : nullptr));
         if (B > Buser) ASM_KL(k_mark_padding<<<(B - Buser + 127) / 128, 128, 0, stream>>>(state.p, Buser, B));
         ASM_CK(cudaGetLastError());
         return ASM_OK;
@@ -1774,7 +1778,15 @@ class LpSolver {
             if (P.engine == 4) return ASM_E_INVALID;
             use_ipm = false;
         }
-        ASM_TRY(precondition(P.ruiz_iters, (!use_ipm && P.warm_start && has_solution) ? (int)P.warm_start : 0));
+        const int warm = (!use_ipm && P.warm_start && has_solution) ? (int)P.warm_start : 0;
+        if (warm) {
+            if (d_prev_ok.n < (size_t)B) ASM_TRY(d_prev_ok.alloc(B));
+            std::vector<int> ok(B, 0);
+            for (int s = 0; s < Buser; ++s) ok[s] = host_state[s].status == ASM_LP_OPTIMAL;
+            ASM_CK(cudaMemcpyAsync(d_prev_ok.p, ok.data(), sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+            ASM_CK(cudaStreamSynchronize(stream));
+        }
+        ASM_TRY(precondition(P.ruiz_iters, warm));
         if (n_masked >= 0) {
             ASM_KL(k_apply_mask<<<(Buser + 127) / 128, 128, 0, stream>>>(state.p, d_active.p, Buser));
             *flag = n_masked;

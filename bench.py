@@ -46,7 +46,7 @@ def parse_args():
                     help="scenarios of the whole job (BASELINE config 5: 1024), split over the GPUs")
     ap.add_argument("--single-case", default="case13659pegase",
                     help="instance of the single-instance metrics reported at N = 1 (sub-LP ms, SLP it/s); 'none' skips them")
-    ap.add_argument("--single-slp-iters", type=int, default=12)
+    ap.add_argument("--single-slp-iters", type=int, default=60)
     ap.add_argument("--eps", type=float, default=5e-7,
                     help="relative KKT tolerance; 5e-7 keeps |pobj - dobj| / |obj| below the 1e-6 parity bar")
     ap.add_argument("--delta", type=float, default=1000.0, help="step bound (Line Search uses 1000, slp.jl:23)")
