@@ -55,6 +55,11 @@ struct IpmState {
     int ncomp, hits, acc_hits, save, bad;
 };
 
+struct KktStepRange {
+    int s0, s1, m0, m1;   // single-term items [s0, s1), multi-term chunks [m0, m1) of a one-step launch
+};
+constexpr int kFusedThreads = 1024;   // block size of the fused walks over runs of narrow steps
+
 struct KktDev {
     const KktTerm *terms;
     const int *fs_beg, *fs_end, *fmstep;
@@ -110,17 +115,19 @@ __device__ __forceinline__ void ldl_apply(const KktDev &d, int tflag, double acc
     }
 }
 template <bool BATCH, bool FUSED>
-__global__ void __launch_bounds__(kThreads) k_ldl_factor(KktDev d, int B, int l0, int l1, const ScenState *st) {
+__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_factor(KktDev d, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
     const bool live = st[s].status < 0;
-    const int first = BATCH ? blockIdx.x * kWarps + warp : blockIdx.x * kThreads + threadIdx.x;
-    const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
+    const int bw = blockDim.x >> 5;   // 8 warps per block for one-step launches, 32 for the fused walks
+    const int first = BATCH ? blockIdx.x * bw + warp : blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = BATCH ? gridDim.x * bw : gridDim.x * blockDim.x;
     for (int l = l0; l < l1; ++l) {
-        if (live) {
-            const int q1 = d.fs_end[l];
+        {   // loads are never gated on the scenario's status (it would put one more dependent load on the critical path); stores are
+            // one-step launches get their ranges as arguments (one dependent load less on the critical path)
+            const int q0 = FUSED ? d.fs_beg[l] : rg.s0, q1 = FUSED ? d.fs_end[l] : rg.s1;
             if (BATCH) {
-                for (int q = d.fs_beg[l] + 4 * first; q < q1; q += 4 * stride) {
+                for (int q = q0 + 4 * first; q < q1; q += 4 * stride) {
                     KktTerm u[4];
                     double a[4], b[4], c[4];
 #pragma unroll
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) k_ldl_factor(KktDev d, int B, int l0
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        if (q + i >= q1) break;
+                        if (q + i >= q1 || !live) break;
                         const double r = tv[i] - a[i] * b[i] * c[i];
                         if ((u[i].t & ~kLastBit) >= d.nnzL) {
                             d.diag0[te[i]] = r;
@@ -153,13 +160,13 @@ __global__ void __launch_bounds__(kThreads) k_ldl_factor(KktDev d, int B, int l0
                     }
                 }
             } else {
-                for (int q = d.fs_beg[l] + first; q < q1; q += stride) {
+                for (int q = q0 + first; q < q1; q += stride) {
                     const KktTerm u = d.terms[q];
-                    ldl_apply(d, u.t, d.W[u.a] * d.W[u.b] * d.invd[u.k], 1, 0);
+                    if (live) ldl_apply(d, u.t, d.W[u.a] * d.W[u.b] * d.invd[u.k], 1, 0);
                 }
             }
-            const int c1 = d.fmstep[l + 1];
-            for (int c = d.fmstep[l] + first; c < c1; c += stride) {
+            const int c0 = FUSED ? d.fmstep[l] : rg.m0, c1 = FUSED ? d.fmstep[l + 1] : rg.m1;
+            for (int c = c0 + first; c < c1; c += stride) {
                 const KktRange r = d.fmchunk[c];
                 KktTerm u = d.terms[r.begin];
                 const int tflag = u.t;
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) k_ldl_factor(KktDev d, int B, int l0
                     u = d.terms[q];
                     acc += d.W[(int64_t)u.a * B + s] * d.W[(int64_t)u.b * B + s] * d.invd[(int64_t)u.k * B + s];
                 }
-                ldl_apply(d, tflag, acc, B, s);
+                if (live) ldl_apply(d, tflag, acc, B, s);
             }
         }
         if (FUSED) __syncthreads();
@@ -177,17 +184,18 @@ __global__ void __launch_bounds__(kThreads) k_ldl_factor(KktDev d, int B, int l0
 
 // forward substitution  v <- L^-1 v  (fan-out, laid out like the factorisation; v indexed by node id, in place)
 template <bool BATCH, bool FUSED>
-__global__ void __launch_bounds__(kThreads) k_ldl_fwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st) {
+__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_fwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
     const bool live = st[s].status < 0;
-    const int first = BATCH ? blockIdx.x * kWarps + warp : blockIdx.x * kThreads + threadIdx.x;
-    const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
+    const int bw = blockDim.x >> 5;   // 8 warps per block for one-step launches, 32 for the fused walks
+    const int first = BATCH ? blockIdx.x * bw + warp : blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = BATCH ? gridDim.x * bw : gridDim.x * blockDim.x;
     for (int l = l0; l < l1; ++l) {
-        if (live) {
-            const int q1 = d.ws_end[l];
+        {   // loads are never gated on the scenario's status (it would put one more dependent load on the critical path); stores are
+            const int q0 = FUSED ? d.ws_beg[l] : rg.s0, q1 = FUSED ? d.ws_end[l] : rg.s1;
             if (BATCH) {
-                for (int q = d.ws_beg[l] + 4 * first; q < q1; q += 4 * stride) {
+                for (int q = q0 + 4 * first; q < q1; q += 4 * stride) {
                     KktFwdItem u[4];
                     double a[4], x[4], c[4], t[4];
 #pragma unroll
@@ -201,16 +209,16 @@ __global__ void __launch_bounds__(kThreads) k_ldl_fwd(KktDev d, double *v, int B
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (q + i < q1) v[(int64_t)u[i].dst * B + s] = t[i] - a[i] * x[i] * c[i];
+                        if (q + i < q1 && live) v[(int64_t)u[i].dst * B + s] = t[i] - a[i] * x[i] * c[i];
                 }
             } else {
-                for (int q = d.ws_beg[l] + first; q < q1; q += stride) {
+                for (int q = q0 + first; q < q1; q += stride) {
                     const KktFwdItem u = d.fwd[q];
-                    v[u.dst] -= d.W[u.pos] * v[u.src] * d.invd[u.k];
+                    if (live) v[u.dst] -= d.W[u.pos] * v[u.src] * d.invd[u.k];
                 }
             }
-            const int c1 = d.wmstep[l + 1];
-            for (int c = d.wmstep[l] + first; c < c1; c += stride) {
+            const int c0 = FUSED ? d.wmstep[l] : rg.m0, c1 = FUSED ? d.wmstep[l + 1] : rg.m1;
+            for (int c = c0 + first; c < c1; c += stride) {
                 const KktRange r = d.wmchunk[c];
                 KktFwdItem u = d.fwd[r.begin];
                 const int dst = u.dst;
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) k_ldl_fwd(KktDev d, double *v, int B
                     u = d.fwd[q];
                     acc += d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s] * d.invd[(int64_t)u.k * B + s];
                 }
-                v[(int64_t)dst * B + s] -= acc;
+                if (live) v[(int64_t)dst * B + s] -= acc;
             }
         }
         if (FUSED) __syncthreads();
@@ -235,17 +243,18 @@ __global__ void __launch_bounds__(kThreads) k_ldl_diag(KktDev d, double *v, int 
 // backward substitution  v <- L'^-1 v : the rows of a column are its ancestors in the elimination tree and sit on
 // distinct levels, so every item of a step has its own target; steps are walked downwards
 template <bool BATCH, bool FUSED>
-__global__ void __launch_bounds__(kThreads) k_ldl_bwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st) {
+__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_bwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
     const bool live = st[s].status < 0;
-    const int first = BATCH ? blockIdx.x * kWarps + warp : blockIdx.x * kThreads + threadIdx.x;
-    const int stride = BATCH ? gridDim.x * kWarps : gridDim.x * kThreads;
+    const int bw = blockDim.x >> 5;   // 8 warps per block for one-step launches, 32 for the fused walks
+    const int first = BATCH ? blockIdx.x * bw + warp : blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = BATCH ? gridDim.x * bw : gridDim.x * blockDim.x;
     for (int l = l1 - 1; l >= l0; --l) {
-        const int q1 = d.bstep[l + 1];
-        if (live) {
+        const int q0 = FUSED ? d.bstep[l] : rg.s0, q1 = FUSED ? d.bstep[l + 1] : rg.s1;
+        {   // loads are never gated on the scenario's status (it would put one more dependent load on the critical path); stores are
             if (BATCH) {
-                for (int q = d.bstep[l] + 4 * first; q < q1; q += 4 * stride) {
+                for (int q = q0 + 4 * first; q < q1; q += 4 * stride) {
                     KktBwdItem u[4];
                     double a[4], x[4], c[4], t[4];
 #pragma unroll
@@ -259,12 +268,12 @@ __global__ void __launch_bounds__(kThreads) k_ldl_bwd(KktDev d, double *v, int B
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (q + i < q1) v[(int64_t)u[i].dst * B + s] = t[i] - c[i] * a[i] * x[i];
+                        if (q + i < q1 && live) v[(int64_t)u[i].dst * B + s] = t[i] - c[i] * a[i] * x[i];
                 }
             } else {
-                for (int q = d.bstep[l] + first; q < q1; q += stride) {
+                for (int q = q0 + first; q < q1; q += stride) {
                     const KktBwdItem u = d.bwd[q];
-                    v[u.dst] -= d.invd[u.k] * d.W[u.pos] * v[u.src];
+                    if (live) v[u.dst] -= d.invd[u.k] * d.W[u.pos] * v[u.src];
                 }
             }
         }
@@ -952,6 +961,13 @@ struct IpmEngine {
         if (g_solve_work) cudaGraphExecDestroy(g_solve_work);
     }
 
+    // steps with at most this many items are walked by one 1024-thread block per 32 scenarios instead of getting a
+    // launch of their own: a launch costs ~4-5 us on the critical path, a pass of the block ~1.5 us
+    static int narrow_for(int B) {
+        const char *e = getenv("ASM_IPM_NARROW");
+        if (e) return atoi(e);
+        return B == 1 ? 2048 : 64;
+    }
     template <class T>
     static int up(DBuf<T> &dst, const std::vector<T> &src) {
         ASM_TRY(dst.alloc(std::max<size_t>(src.size(), 1)));
@@ -968,7 +984,7 @@ struct IpmEngine {
                 return fail(ASM_E_INVALID, "duplicate (row, column) entries in the pattern: the barrier engine needs a deduplicated CSR");
         }
         const auto t0 = std::chrono::steady_clock::now();
-        if (sym.build(n, m, row_ptr.data(), col_idx.data(), B == 1 ? 2048 : 64))
+        if (sym.build(n, m, row_ptr.data(), col_idx.data(), narrow_for(B)))
             return fail(ASM_E_INVALID, "KKT symbolic analysis failed (index out of range or more than 2^31 update terms)");
         symbolic_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         ASM_TRY(up(terms, sym.terms));
@@ -1074,16 +1090,17 @@ struct IpmEngine {
         count += 2;
         for (const KktLaunch &L : sym.flaunch) {
             const dim3 grid = level_grid(L);
+            const KktStepRange rg = {sym.fs_beg[L.l0], sym.fs_end[L.l0], sym.fmstep[L.l0], sym.fmstep[L.l0 + 1]};
             if (B > 1) {
                 if (L.fused)
-                    k_ldl_factor<true, true><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state);
+                    k_ldl_factor<true, true><<<grid, kFusedThreads, 0, st>>>(d, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_factor<true, false><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state);
+                    k_ldl_factor<true, false><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state, rg);
             } else {
                 if (L.fused)
-                    k_ldl_factor<false, true><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state);
+                    k_ldl_factor<false, true><<<grid, kFusedThreads, 0, st>>>(d, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_factor<false, false><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state);
+                    k_ldl_factor<false, false><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state, rg);
             }
             ++count;
         }
@@ -1092,16 +1109,17 @@ struct IpmEngine {
         KktDev d = dev();
         for (const KktLaunch &L : sym.wlaunch) {
             const dim3 grid = level_grid(L);
+            const KktStepRange rg = {sym.ws_beg[L.l0], sym.ws_end[L.l0], sym.wmstep[L.l0], sym.wmstep[L.l0 + 1]};
             if (B > 1) {
                 if (L.fused)
-                    k_ldl_fwd<true, true><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                    k_ldl_fwd<true, true><<<grid, kFusedThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_fwd<true, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                    k_ldl_fwd<true, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
             } else {
                 if (L.fused)
-                    k_ldl_fwd<false, true><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                    k_ldl_fwd<false, true><<<grid, kFusedThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_fwd<false, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                    k_ldl_fwd<false, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
             }
             ++count;
         }
@@ -1116,16 +1134,17 @@ struct IpmEngine {
         for (auto it = sym.blaunch.rbegin(); it != sym.blaunch.rend(); ++it) {
             const KktLaunch &L = *it;
             const dim3 grid = level_grid(L);
+            const KktStepRange rg = {sym.bstep[L.l0], sym.bstep[L.l0 + 1], 0, 0};
             if (B > 1) {
                 if (L.fused)
-                    k_ldl_bwd<true, true><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                    k_ldl_bwd<true, true><<<grid, kFusedThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_bwd<true, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                    k_ldl_bwd<true, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
             } else {
                 if (L.fused)
-                    k_ldl_bwd<false, true><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                    k_ldl_bwd<false, true><<<grid, kFusedThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_bwd<false, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state);
+                    k_ldl_bwd<false, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
             }
             ++count;
         }
