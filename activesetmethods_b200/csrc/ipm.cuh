@@ -51,7 +51,6 @@ struct IpmState {
     double mu, smu, ap, ad, qs, q_un;
     double ray_obj, ray_kty;  // Farkas test of the last step direction dy (normalised)
     double kept[5];           // pobj, dobj, pres, dres, gap of the point kept by k_ipm_save
-    double pres_prev, dres_prev;  // residuals of the previous step (to judge the accuracy of the linear solves)
     int ncomp, hits, acc_hits, save, bad;
 };
 
@@ -82,7 +81,7 @@ struct IpmView {
     // KKT vectors (node order: columns then rows)
     double *rhs0, *sol, *work;
     IpmState *ist;
-    int *need_refine;     // scenarios whose last step did not reduce the residuals as an exact Newton step would
+    int *need_refine;     // counts LPs that sit at the acceptable level without reaching the target (see k_ipm_decide)
     const double *c0;     // objective constants (the termination test is relative to the objective the caller sees)
     double delta, prox;
     double eps, eps_acc;  // target tolerance; acceptable tolerance (kept as a fall-back result when the target is not reached)
@@ -395,7 +394,6 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_init_state(LpView v, IpmV
     it.save = 0;
     it.ray_obj = -1.0;
     it.ray_kty = 1.0;
-    it.pres_prev = it.dres_prev = -1.0;
     it.bad = (badc + badr) > 0.0;
     g.ist[s] = it;
     if (st->status < 0 && it.bad) {  // lb > ub or rl > ru: nothing to iterate on
@@ -498,15 +496,6 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
     st.dres = sqrt(q[I_RLP2] + q[I_RDW2]);
     st.gap = fabs(st.pobj - st.dobj);
     st.total = iter;
-    // An exact Newton step of length a leaves (1 - a) of the linear residuals.  A long step that leaves more than half
-    // of them means the linear solves are not accurate enough: ask the host for another refinement pass.
-    if (it.pres_prev >= 0.0 && iter >= 8) {   // the first steps, far from the central path, say little
-        const bool p_bad = it.ap > 0.5 && pres > 0.5 * it.pres_prev + 0.5 * g.eps * (1.0 + st.nq_un);
-        const bool d_bad = it.ad > 0.5 && dres > 0.5 * it.dres_prev + 0.5 * g.eps * (1.0 + st.nc_un);
-        if (p_bad || d_bad) atomicAdd(g.need_refine, 1);
-    }
-    it.pres_prev = pres;
-    it.dres_prev = dres;
     const double c0 = g.c0[s];
     const double gden = 1.0 + fabs(pq + c0) + fabs(dq + c0);
     auto within = [&](double e) {
@@ -527,8 +516,13 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
     } else if (it.hits > 0) {
         status = ASM_LP_OPTIMAL;  // the point saved at the previous step stands
     } else if (acc) {
-        it.acc_hits += 1;         // fall-back result should the target tolerance not be reached
+        // acceptable but not at the target: keep the point as fall-back result.  When that lasts, the accuracy of the
+        // linear solves is what holds the last digits back (the gap inherits |x| times the dual residual): ask the host
+        // for one more refinement pass after 3 and after 6 such steps, and settle for the acceptable point after 10.
+        it.acc_hits += 1;
         it.save = 1;
+        if (it.acc_hits == 3 || it.acc_hits == 6) atomicAdd(g.need_refine, 1);
+        if (it.acc_hits >= 10) status = ASM_LP_OPTIMAL;
     } else if (nan) {
         status = it.acc_hits > 0 ? ASM_LP_OPTIMAL : ASM_LP_NUMERICAL_ERROR;
     } else {
@@ -567,7 +561,10 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
     // the duality gap q |x|^2 below prox (1 + 2 |c'x|)
     {
         const double xn = fmax(1.0, sqrt(q[I_XN2]));
-        it.q_un = g.prox * fmin(0.5 * (1.0 + st.nc_un) / xn, (1.0 + 2.0 * fabs(st.pobj)) / (xn * xn));
+        const double qn = g.prox * fmin(0.5 * (1.0 + st.nc_un) / xn, (1.0 + 2.0 * fabs(st.pobj)) / (xn * xn));
+        // hysteresis: a weight that drifts by a percent per step re-introduces a dual residual of that size at every
+        // step and the last digits never settle (seen on restoration LPs: the gap stalled at 8e-8)
+        if (!(qn > 0.5 * it.q_un && qn < 2.0 * it.q_un)) it.q_un = qn;
         it.qs = it.q_un * st.sc / st.sb;
     }
     g.ist[s] = it;

@@ -1563,10 +1563,10 @@ class LpSolver {
         g.c0 = c0.p;
         KktDev d = E.dev();
         const Geo gr = geo_for(m, B), gc = geo_for(n, B), gm = geo_for(std::max(n, m), B), gN = geo_for((int64_t)n + m, B);
-        // refinement passes per linear solve: fixed when ipm_refine >= 0, else adaptive -- one, and a second one from the
-        // moment a long Newton step fails to halve the linear residuals (k_ipm_decide counts those)
+        // refinement passes per linear solve: ipm_refine to start with (default 1), one more (at most two more) each time
+        // k_ipm_decide reports LPs stuck between the acceptable and the target tolerance
         int refine = P.ipm_refine >= 0 ? P.ipm_refine : 1;
-        const bool adaptive = P.ipm_refine < 0;
+        const int refine_max = refine + 2;
         g.need_refine = n_active.p + 1;
         flag[1] = 0;
         ASM_CK(cudaMemcpyAsync(n_active.p + 1, flag + 1, sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1602,9 +1602,9 @@ class LpSolver {
             ASM_CK(cudaMemcpyAsync(flag, n_active.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
             ASM_CK(cudaStreamSynchronize(stream));
             if (*flag <= 0 || it >= max_it) break;
-            if (adaptive && flag[1] > refine_seen && refine < 2) {
+            if (flag[1] > refine_seen && refine < refine_max) {
                 ++refine;
-                if (trace) fprintf(stderr, "[asm] barrier engine: step %d, %d inexact steps so far -> %d refinement pass(es)\n", it, flag[1], refine);
+                if (trace) fprintf(stderr, "[asm] barrier engine: step %d, %d LPs stuck at the acceptable level -> %d refinement passes\n", it, flag[1], refine);
             }
             refine_seen = flag[1];
             ASM_KB(k_ipm_diag, gm, v, g, d);

@@ -314,3 +314,65 @@ def test_generic_lp_against_highs(gpu):
         assert abs(info["objective"] - obj) <= OBJ_RTOL * max(1.0, abs(obj))
         assert lp_feasibility(K, lp.primal(), lb, ub, rl, ru) <= FEAS_TOL
         lp.close()
+
+
+def test_set_active_masks_scenarios(gpu):
+    """asm_slp_set_active: masked scenarios cost nothing and come back SKIPPED with zeroed outputs, the others are
+    solved exactly as in the unmasked batch (what the lock-step SLP driver does for finished / other-phase scenarios)."""
+    from activesetmethods_b200.examples import acopf
+    from activesetmethods_b200.sublp import SubLp
+    net = acopf.case9()
+    B = 40
+    mdls = [acopf.AcopfModel(acopf.perturb_loads(net, s + 1)) for s in range(B)]
+    m0 = mdls[0]
+    arr = lambda f: np.array([f(m) for m in mdls])   # noqa: E731
+    x = arr(lambda m: np.clip(m.x0, m.x_L, m.x_U))
+    args = (x, np.array([m.eval_f(xx) for m, xx in zip(mdls, x)]),
+            np.array([m.eval_grad_f(xx, np.zeros(m.n)) for m, xx in zip(mdls, x)]),
+            np.array([m.eval_g(xx, np.zeros(m.m)) for m, xx in zip(mdls, x)]),
+            np.array([m.eval_jac_g(xx, "eval", None, None, np.zeros(m.nnz)) for m, xx in zip(mdls, x)]), 1000.0, False)
+    lp = SubLp(m0.n, m0.m, m0.j_str, arr(lambda m: m.x_L), arr(lambda m: m.x_U), arr(lambda m: m.g_L),
+               arr(lambda m: m.g_U), batch=B)
+    full = lp.sub_optimize(*args)
+    obj_full = np.array([i["objective"] for i in lp.last_info])
+    mask = np.zeros(B, dtype=bool)
+    mask[[0, 3, 17, 39]] = True
+    lp.set_active(mask)
+    part = lp.sub_optimize(*args)
+    st = np.array([i["status"] for i in lp.last_info])
+    assert np.all(st[mask] == 0) and np.all(st[~mask] == 5)
+    assert np.all(part[5][~mask] == 5) and not part[0][~mask].any() and not part[1][~mask].any()
+    obj_part = np.array([i["objective"] for i in lp.last_info])
+    assert np.allclose(obj_part[mask], obj_full[mask], rtol=1e-12, atol=0)
+    assert np.allclose(part[0][mask], full[0][mask], rtol=0, atol=1e-9)
+    lp.set_active(None)
+    again = lp.sub_optimize(*args)
+    assert np.all(again[5] == 0)
+    lp.close()
+
+
+def test_pageable_and_pinned_inputs_agree(gpu):
+    """Host arrays go straight to the device when the caller pinned them and through the handle's pinned ring when they
+    are pageable (util.cuh PinnedRing): same bits either way, also for inputs larger than one ring chunk."""
+    import torch
+    from activesetmethods_b200.sublp import SubLp
+    pr = problem("case118")
+    B = 96                                            # dE: 96 x 6297 x 8 B = 4.8 MB; two arrays exceed a ring chunk together
+    x = np.clip(pr.x0, pr.x_L, pr.x_U)
+    one = dict(x=x, f=pr.eval_f(x), df=pr.eval_grad_f(x, np.zeros(pr.n)), E=pr.eval_g(x, np.zeros(pr.m)),
+               dE=pr.eval_jac_g(x, "eval", None, None, np.zeros(len(pr.j_str))))
+    rng = np.random.default_rng(0)
+    scale = 1.0 + 1e-3 * rng.standard_normal((B, 1))
+    big = {k: np.ascontiguousarray(np.repeat(np.atleast_2d(v), B, axis=0) * (scale if k in ("df", "dE") else 1.0))
+           for k, v in one.items() if k != "f"}
+    f = np.full(B, one["f"])
+    lp = SubLp(pr.n, pr.m, pr.j_str, pr.x_L, pr.x_U, pr.g_L, pr.g_U, batch=B)
+    lp.update(big["x"], f, big["df"], big["E"], big["dE"], 1000.0, False)
+    v_pageable = lp.jacobian_csr(7)[2].copy()
+    pinned = {k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in big.items()}
+    lp.update(pinned["x"], f, pinned["df"], pinned["E"], pinned["dE"], 1000.0, False)
+    v_pinned = lp.jacobian_csr(7)[2].copy()
+    assert np.array_equal(v_pageable, v_pinned)
+    pat = so.JacobianPattern(pr.m, pr.n, pr.j_str)
+    assert np.array_equal(v_pinned, pat.assemble(big["dE"][7]))
+    lp.close()
