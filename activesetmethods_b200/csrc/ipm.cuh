@@ -518,11 +518,11 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
     } else if (acc) {
         // acceptable but not at the target: keep the point as fall-back result.  When that lasts, the accuracy of the
         // linear solves is what holds the last digits back (the gap inherits |x| times the dual residual): ask the host
-        // for one more refinement pass after 3 and after 6 such steps, and settle for the acceptable point after 10.
+        // for one more refinement pass after 5 and after 8 such steps, and settle for the acceptable point after 12.
         it.acc_hits += 1;
         it.save = 1;
-        if (it.acc_hits == 3 || it.acc_hits == 6) atomicAdd(g.need_refine, 1);
-        if (it.acc_hits >= 10) status = ASM_LP_OPTIMAL;
+        if (it.acc_hits == 5 || it.acc_hits == 8) atomicAdd(g.need_refine, 1);
+        if (it.acc_hits >= 12) status = ASM_LP_OPTIMAL;
     } else if (nan) {
         status = it.acc_hits > 0 ? ASM_LP_OPTIMAL : ASM_LP_NUMERICAL_ERROR;
     } else {

@@ -76,11 +76,15 @@ def test_config2_case118_line_search_tight(gpu):
 
 @pytest.mark.parametrize("name", ["hs071", "case9"])
 def test_trust_region_tight_objective(gpu, name):
-    pr, slp = _gpu(name, "Trust Region", 300, **TIGHT)
-    ref = _oracle(name, "Trust Region", 300, **TIGHT)
+    # 120 iterations: both sides have converged to 1e-12 by then; the reference's trust-region loop has no lower bound on
+    # Delta, and a run that misses its KKT exit keeps dividing Delta by 10 (1e-96 after 250 iterations) until an LP fails
+    pr, slp = _gpu(name, "Trust Region", 120, **TIGHT)
+    ref = _oracle(name, "Trust Region", 120, **TIGHT)
     rel = abs(slp.obj_val - ref.obj_val) / max(1.0, abs(ref.obj_val))
     print(f"{name} TR tight: gpu ret {slp.ret} it {slp.iter} obj {slp.obj_val:.9f} viol {_viol(pr, slp.x):.2e} | "
           f"oracle ret {ref.ret} it {ref.iter} obj {ref.obj_val:.9f} viol {ref.prim_infeas:.2e} | rel {rel:.2e}")
+    bad = [(k, e) for k, e in enumerate(slp.lp_log) if e[0] not in (0, 1)]
+    assert not bad, bad
     assert rel <= 1e-6
     assert _viol(pr, slp.x) <= 1e-6 and ref.prim_infeas <= 1e-6
     # a feasible point on both sides: 0 / 6, or -1 when max_iter cut a run whose point is already feasible to 1e-6
