@@ -54,6 +54,12 @@ struct IpmState {
     int ncomp, hits, acc_hits, save, bad;
 };
 
+// Programmatic dependent launch: a step's grid may be scheduled while the previous step still runs (the launch latency
+// and its index loads leave the critical path); it must not touch W, 1/d, the pivots or the right-hand side before
+// pdl_wait(), which returns when the previous grid has completed and its stores are visible.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct KktStepRange {
     int s0, s1, m0, m1;   // single-term items [s0, s1), multi-term chunks [m0, m1) of a one-step launch
 };
@@ -115,6 +121,7 @@ __device__ __forceinline__ void ldl_apply(const KktDev &d, int tflag, double acc
 }
 template <bool BATCH, bool FUSED>
 __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_factor(KktDev d, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
     const bool live = st[s].status < 0;
@@ -126,6 +133,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_factor
             // one-step launches get their ranges as arguments (one dependent load less on the critical path)
             const int q0 = FUSED ? d.fs_beg[l] : rg.s0, q1 = FUSED ? d.fs_end[l] : rg.s1;
             if (BATCH) {
+                if (l == l0) pdl_wait();
                 for (int q = q0 + 4 * first; q < q1; q += 4 * stride) {
                     KktTerm u[4];
                     double a[4], b[4], c[4];
@@ -159,6 +167,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_factor
                     }
                 }
             } else {
+                if (l == l0) pdl_wait();
                 for (int q = q0 + first; q < q1; q += stride) {
                     const KktTerm u = d.terms[q];
                     if (live) ldl_apply(d, u.t, d.W[u.a] * d.W[u.b] * d.invd[u.k], 1, 0);
@@ -184,6 +193,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_factor
 // forward substitution  v <- L^-1 v  (fan-out, laid out like the factorisation; v indexed by node id, in place)
 template <bool BATCH, bool FUSED>
 __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_fwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
     const bool live = st[s].status < 0;
@@ -194,23 +204,36 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_fwd(Kk
         {   // loads are never gated on the scenario's status (it would put one more dependent load on the critical path); stores are
             const int q0 = FUSED ? d.ws_beg[l] : rg.s0, q1 = FUSED ? d.ws_end[l] : rg.s1;
             if (BATCH) {
-                for (int q = q0 + 4 * first; q < q1; q += 4 * stride) {
-                    KktFwdItem u[4];
-                    double a[4], x[4], c[4], t[4];
+                int q = q0 + 4 * first;
+                KktFwdItem u[4];
+                if (q < q1) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) u[i] = d.fwd[q + i < q1 ? q + i : q];
+                }
+                if (l == l0) pdl_wait();
+                while (q < q1) {
+                    double a[4], x[4], c[4], t[4];
+                    int dst[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         a[i] = d.W[(int64_t)u[i].pos * B + s];
                         x[i] = v[(int64_t)u[i].src * B + s];
                         c[i] = d.invd[(int64_t)u[i].k * B + s];
                         t[i] = v[(int64_t)u[i].dst * B + s];
+                        dst[i] = u[i].dst;
+                    }
+                    const int qn = q + 4 * stride;
+                    if (qn < q1) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) u[i] = d.fwd[qn + i < q1 ? qn + i : qn];
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (q + i < q1 && live) v[(int64_t)u[i].dst * B + s] = t[i] - a[i] * x[i] * c[i];
+                        if (q + i < q1 && live) v[(int64_t)dst[i] * B + s] = t[i] - a[i] * x[i] * c[i];
+                    q = qn;
                 }
             } else {
+                if (l == l0) pdl_wait();
                 for (int q = q0 + first; q < q1; q += stride) {
                     const KktFwdItem u = d.fwd[q];
                     if (live) v[u.dst] -= d.W[u.pos] * v[u.src] * d.invd[u.k];
@@ -243,6 +266,7 @@ __global__ void __launch_bounds__(kThreads) k_ldl_diag(KktDev d, double *v, int 
 // distinct levels, so every item of a step has its own target; steps are walked downwards
 template <bool BATCH, bool FUSED>
 __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_bwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
     const bool live = st[s].status < 0;
@@ -253,23 +277,36 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_bwd(Kk
         const int q0 = FUSED ? d.bstep[l] : rg.s0, q1 = FUSED ? d.bstep[l + 1] : rg.s1;
         {   // loads are never gated on the scenario's status (it would put one more dependent load on the critical path); stores are
             if (BATCH) {
-                for (int q = q0 + 4 * first; q < q1; q += 4 * stride) {
-                    KktBwdItem u[4];
-                    double a[4], x[4], c[4], t[4];
+                int q = q0 + 4 * first;
+                KktBwdItem u[4];
+                if (q < q1) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) u[i] = d.bwd[q + i < q1 ? q + i : q];
+                }
+                if (l == l1 - 1) pdl_wait();
+                while (q < q1) {
+                    double a[4], x[4], c[4], t[4];
+                    int dst[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         a[i] = d.W[(int64_t)u[i].pos * B + s];
                         x[i] = v[(int64_t)u[i].src * B + s];
                         c[i] = d.invd[(int64_t)u[i].k * B + s];
                         t[i] = v[(int64_t)u[i].dst * B + s];
+                        dst[i] = u[i].dst;
+                    }
+                    const int qn = q + 4 * stride;
+                    if (qn < q1) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) u[i] = d.bwd[qn + i < q1 ? qn + i : qn];
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (q + i < q1 && live) v[(int64_t)u[i].dst * B + s] = t[i] - c[i] * a[i] * x[i];
+                        if (q + i < q1 && live) v[(int64_t)dst[i] * B + s] = t[i] - c[i] * a[i] * x[i];
+                    q = qn;
                 }
             } else {
+                if (l == l1 - 1) pdl_wait();
                 for (int q = q0 + first; q < q1; q += stride) {
                     const KktBwdItem u = d.bwd[q];
                     if (live) v[u.dst] -= d.invd[u.k] * d.W[u.pos] * v[u.src];
@@ -1061,6 +1098,22 @@ struct IpmEngine {
         return g;
     }
 
+    // launch of a step kernel, as a programmatic dependent of the previous one (see pdl_wait)
+    bool use_pdl = getenv("ASM_NO_PDL") == nullptr;
+    template <class... KArgs, class... Args>
+    void launch_step(void (*kern)(KArgs...), dim3 grid, int block, cudaStream_t st, Args... args) const {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(block);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = use_pdl ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    }
     // grid of a step kernel.  Batch: a warp per item, scenarios over blockIdx.y; single LP: a thread per item
     dim3 level_grid(const KktLaunch &L) const {
         unsigned gx = 1;
@@ -1090,14 +1143,14 @@ struct IpmEngine {
             const KktStepRange rg = {sym.fs_beg[L.l0], sym.fs_end[L.l0], sym.fmstep[L.l0], sym.fmstep[L.l0 + 1]};
             if (B > 1) {
                 if (L.fused)
-                    k_ldl_factor<true, true><<<grid, kFusedThreads, 0, st>>>(d, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_factor<true, true>, grid, kFusedThreads, st, d, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_factor<true, false><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_factor<true, false>, grid, kThreads, st, d, B, L.l0, L.l1, v.state, rg);
             } else {
                 if (L.fused)
-                    k_ldl_factor<false, true><<<grid, kFusedThreads, 0, st>>>(d, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_factor<false, true>, grid, kFusedThreads, st, d, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_factor<false, false><<<grid, kThreads, 0, st>>>(d, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_factor<false, false>, grid, kThreads, st, d, B, L.l0, L.l1, v.state, rg);
             }
             ++count;
         }
@@ -1109,14 +1162,14 @@ struct IpmEngine {
             const KktStepRange rg = {sym.ws_beg[L.l0], sym.ws_end[L.l0], sym.wmstep[L.l0], sym.wmstep[L.l0 + 1]};
             if (B > 1) {
                 if (L.fused)
-                    k_ldl_fwd<true, true><<<grid, kFusedThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_fwd<true, true>, grid, kFusedThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_fwd<true, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_fwd<true, false>, grid, kThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);
             } else {
                 if (L.fused)
-                    k_ldl_fwd<false, true><<<grid, kFusedThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_fwd<false, true>, grid, kFusedThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_fwd<false, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_fwd<false, false>, grid, kThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);
             }
             ++count;
         }
@@ -1134,14 +1187,14 @@ struct IpmEngine {
             const KktStepRange rg = {sym.bstep[L.l0], sym.bstep[L.l0 + 1], 0, 0};
             if (B > 1) {
                 if (L.fused)
-                    k_ldl_bwd<true, true><<<grid, kFusedThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_bwd<true, true>, grid, kFusedThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_bwd<true, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_bwd<true, false>, grid, kThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);
             } else {
                 if (L.fused)
-                    k_ldl_bwd<false, true><<<grid, kFusedThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_bwd<false, true>, grid, kFusedThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);
                 else
-                    k_ldl_bwd<false, false><<<grid, kThreads, 0, st>>>(d, vec, B, L.l0, L.l1, v.state, rg);
+                    launch_step(k_ldl_bwd<false, false>, grid, kThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);
             }
             ++count;
         }
