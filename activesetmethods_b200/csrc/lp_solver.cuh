@@ -1566,7 +1566,7 @@ class LpSolver {
         // refinement passes per linear solve: ipm_refine to start with (default 1), one more (at most two more) each time
         // k_ipm_decide reports LPs stuck between the acceptable and the target tolerance
         int refine = P.ipm_refine >= 0 ? P.ipm_refine : 1;
-        const int refine_max = refine + 2;
+        const int base_refine = refine, refine_max = refine + 2;
         g.need_refine = n_active.p + 1;
         flag[1] = 0;
         ASM_CK(cudaMemcpyAsync(n_active.p + 1, flag + 1, sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1577,11 +1577,11 @@ class LpSolver {
         ASM_TRY(E.capture(stream, &E.g_solve_work, E.launches_solve, [&](int64_t &c) { E.enqueue_solve(v, g.work, stream, c); }));
         E.last_pairs = 0;
         E.last_factorisations = 0;
-        auto solve_refined = [&]() -> int {
-            E.last_pairs += 1 + refine;
+        auto solve_refined = [&](int passes) -> int {
+            E.last_pairs += 1 + passes;
             ASM_CK(cudaGraphLaunch(E.g_solve_sol, stream));
             launches += E.launches_solve;
-            for (int r = 0; r < refine; ++r) {
+            for (int r = 0; r < passes; ++r) {
                 ASM_KB(k_kkt_res_cols, gc, v, g);
                 ASM_KB(k_kkt_res_rows, gr, v, g);
                 ASM_CK(cudaGraphLaunch(E.g_solve_work, stream));
@@ -1619,7 +1619,9 @@ class LpSolver {
             E.last_factorisations += 1;
             if (timed) cudaEventRecord(te[1], stream);
             ASM_KB2(k_ipm_rhs, false, gm, v, g);
-            ASM_TRY(solve_refined());
+            // the affine direction only sets the centring parameter and the second-order term: it is not refined
+            // unless the LPs are already stuck on solve accuracy
+            ASM_TRY(solve_refined(refine > base_refine ? refine : 0));
             if (timed) {
                 cudaEventRecord(te[2], stream);
                 cudaEventSynchronize(te[2]);
@@ -1637,7 +1639,7 @@ class LpSolver {
             ASM_KB(k_ipm_muaff, gm, v, g);
             ASM_KL(k_ipm_scalars<<<B, kFinalThreads, 0, stream>>>(v, g, 1, (int)gm.grid.x));
             ASM_KB2(k_ipm_rhs, true, gm, v, g);
-            ASM_TRY(solve_refined());
+            ASM_TRY(solve_refined(refine));
             ASM_KB2(k_ipm_dirs_cols, true, gc, v, g);
             ASM_KB2(k_ipm_dirs_rows, true, gr, v, g);
             ASM_KB(k_ipm_ray, gr, v, g);
