@@ -120,7 +120,7 @@ __device__ __forceinline__ void ldl_apply(const KktDev &d, int tflag, double acc
     }
 }
 template <bool BATCH, bool FUSED>
-__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_factor(KktDev d, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
+__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 4) k_ldl_factor(KktDev d, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
     pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_factor
 
 // forward substitution  v <- L^-1 v  (fan-out, laid out like the factorisation; v indexed by node id, in place)
 template <bool BATCH, bool FUSED>
-__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_fwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
+__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 4) k_ldl_fwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
     pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) k_ldl_diag(KktDev d, double *v, int 
 // backward substitution  v <- L'^-1 v : the rows of a column are its ancestors in the elimination tree and sit on
 // distinct levels, so every item of a step has its own target; steps are walked downwards
 template <bool BATCH, bool FUSED>
-__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads) k_ldl_bwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
+__global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 4) k_ldl_bwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
     pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = BATCH ? blockIdx.y * 32 + lane : 0;
