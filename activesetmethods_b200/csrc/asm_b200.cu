@@ -935,7 +935,7 @@ void asm_lp_default_params(asm_lp_params *p) {
     p->group_size = 0;
     p->hand_over = 0.5;
     p->ipm_max_iter = 200;
-    p->ipm_refine = 1;
+    p->ipm_refine = 0;
     p->ipm_reg = 1e-8;
     p->ipm_prox = 1e-7;
 }

@@ -1565,7 +1565,7 @@ class LpSolver {
         const Geo gr = geo_for(m, B), gc = geo_for(n, B), gm = geo_for(std::max(n, m), B), gN = geo_for((int64_t)n + m, B);
         // refinement passes per linear solve: ipm_refine to start with (default 1), one more (at most two more) each time
         // k_ipm_decide reports LPs stuck between the acceptable and the target tolerance
-        int refine = P.ipm_refine >= 0 ? P.ipm_refine : 1;
+        int refine = P.ipm_refine >= 0 ? P.ipm_refine : 0;
         const int base_refine = refine, refine_max = refine + 2;
         g.need_refine = n_active.p + 1;
         flag[1] = 0;

@@ -79,8 +79,9 @@ typedef struct asm_lp_params {
                            /* empty by the equilibration (0 = default 1e-8)                                            */
     /* barrier engine (engine 0 / 4) */
     int32_t ipm_max_iter;  /* Newton steps per LP (default 200)                                                        */
-    int32_t ipm_refine;    /* iterative-refinement passes per linear solve to start with (default 1); one more, at     */
-                           /* most two more, when LPs sit between the acceptable and the target tolerance              */
+    int32_t ipm_refine;    /* iterative-refinement passes per linear solve to start with (default 0: the barrier       */
+                           /* method tolerates the 1e-8 regularisation error); one more, at most two more, when LPs    */
+                           /* sit between the acceptable and the target tolerance                                      */
     double ipm_reg;        /* static regularisation d of the quasi-definite system (default 1e-8, scaled units)        */
     double ipm_prox;       /* least-norm selection: proximal weight q = ipm_prox (1 + |c|) / (2 max(1, |x|)), i.e. the */
                            /* relative dual residual it may leave in the LP (default 1e-7; 0 = pure LP)                */

@@ -28,7 +28,7 @@ def test_default_params(built_lib):
     p = capi.default_params()
     assert p.eps_rel == 1e-8 and p.check_every == 64 and p.max_iter == 2000000
     assert C.sizeof(capi.LpParams) == 8 * 2 + 8 + 4 * 4 + 8 * 6 + 8 * 4 + 4 * 2 + 8 * 2
-    assert p.ipm_max_iter == 200 and p.ipm_refine == 1 and p.ipm_reg == 1e-8 and p.ipm_prox == 1e-7
+    assert p.ipm_max_iter == 200 and p.ipm_refine == 0 and p.ipm_reg == 1e-8 and p.ipm_prox == 1e-7
     assert C.sizeof(capi.LpInfo) == 4 + 4 + 8 + 8 * 5
 
 
