@@ -573,6 +573,9 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_decide(LpView v, IpmView 
         }
         if (status < 0 && it.acc_hits == 0 && it.ray_obj > v.prm->eps_infeas * fmax(1.0, it.ray_kty)) status = ASM_LP_INFEASIBLE;
     }
+    // safety net: an LP that is still short of the acceptable level after 40 (60) Newton steps is most likely held
+    // back by the accuracy of the linear solves as well
+    if (status < 0 && it.acc_hits == 0 && (iter == 40 || iter == 60)) atomicAdd(g.need_refine, 1);
     if (status < 0 && last) {
         status = it.acc_hits > 0 ? ASM_LP_OPTIMAL : ASM_LP_ITERATION_LIMIT;
         if (it.acc_hits == 0) it.save = 1;
