@@ -7,14 +7,16 @@
 // 20 - 40 Newton steps, and every Newton step of every LP of a batch and of every SLP iteration factorises a matrix
 // with the SAME sparsity pattern (the Jacobian pattern is uploaded once, src/model.jl:10).  So:
 //   * symbolic work once per handle on the host (kkt_symbolic.hpp): ordering, pattern of L, level schedule, the
-//     list of products behind every entry of L;
-//   * numeric L D L' of the quasi-definite system  [-(Dx + d) K'; K (Ew + d)]  on the device, one independent dot
-//     product per entry of L (k_ldl_factor), scenarios across the lanes of a warp (element-major v[i * B + s]:
-//     index loads are warp-uniform, value loads coalesced), no pivoting, no atomics, bit-reproducible;
-//   * level-scheduled substitutions (k_ldl_fwd / k_ldl_bwd) and iterative refinement against the unregularised
-//     matrix (k_kkt_res_*);
+//     fan-out lists of update products grouped by the level of their source column;
+//   * numeric L D L' of the quasi-definite system  [-(Dx + d) K'; K (Ew + d)]  on the device, one launch per level
+//     (k_ldl_factor), every target written by exactly one thread per level, scenarios across the lanes of a warp
+//     (element-major v[i * B + s]: index loads are warp-uniform, value loads coalesced); no pivoting, no atomics,
+//     bit-reproducible;
+//   * level-scheduled substitutions (k_ldl_fwd / k_ldl_diag / k_ldl_bwd), iterative refinement against the
+//     unregularised matrix on demand (k_kkt_res_*); the level kernels are programmatic dependents of one another
+//     and the three launch sequences are captured once as CUDA graphs;
 //   * Mehrotra predictor-corrector with every scalar decision taken on the device per scenario (k_ipm_decide,
-//     k_ipm_scalars); the host enqueues a fixed kernel sequence per Newton step and reads one 4-byte counter.
+//     k_ipm_scalars); the host enqueues a fixed kernel sequence per Newton step and reads two 4-byte counters.
 // A small proximal term (q/2)|x|^2 selects the least-norm optimal step among the minimisers (restoration LPs,
 // min sum of slacks, always have a face of them); q is sized so that the dual residual and the duality gap it leaves
 // in the LP stay below ipm_prox relative (for q below a threshold the minimiser is an exact LP solution anyway:
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(kFinalThreads) k_ipm_init_state(LpView v, IpmV
     it.save = 0;
     it.ray_obj = -1.0;
     it.ray_kty = 1.0;
+    for (double &k : it.kept) k = 0.0;
     it.bad = (badc + badr) > 0.0;
     g.ist[s] = it;
     if (st->status < 0 && it.bad) {  // lb > ub or rl > ru: nothing to iterate on
