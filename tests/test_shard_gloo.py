@@ -67,3 +67,15 @@ def test_block_helpers():
     parts = shard.split_scenarios(10, 4)
     assert [len(p) for p in parts] == [3, 3, 2, 2] and sum(parts, []) == list(range(1, 11))
     assert shard.max_over_ranks(3.5) == 3.5            # no process group: identity
+
+
+def test_strong_scaling_split_is_the_bench_partition():
+    """bench.py's job: 1024 scenarios split over 1 / 2 / 4 / 8 ranks -- contiguous, disjoint, complete, equal sizes."""
+    for world in (1, 2, 4, 8):
+        parts = shard.split_scenarios(1024, world)
+        assert len(parts) == world and all(len(p) == 1024 // world for p in parts)
+        assert sum(parts, []) == list(range(1, 1025))
+    parts = shard.split_scenarios(1000, 8)                 # not divisible: sizes differ by at most one
+    assert sorted(set(len(p) for p in parts)) == [125] and sum(parts, []) == list(range(1, 1001))
+    parts = shard.split_scenarios(1001, 8)
+    assert max(len(p) for p in parts) - min(len(p) for p in parts) == 1 and sum(len(p) for p in parts) == 1001
