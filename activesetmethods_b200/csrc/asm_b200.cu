@@ -1645,7 +1645,8 @@ int asm_kkt_selftest(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, con
     for (int i = 0; i <= n_rows; ++i) rp[i] = (int)row_ptr[i];
     for (int64_t k = 0; k < nnz; ++k) ci[k] = col_idx[k];
     KktSymbolic S;
-    if (S.build(n_cols, n_rows, rp.data(), ci.data())) return fail(ASM_E_INVALID, "symbolic analysis failed");
+    // supernodes as a batch handle would use them (ASM_IPM_SUPERNODE=1 turns them off)
+    if (S.build(n_cols, n_rows, rp.data(), ci.data(), 64, IpmEngine::supernode_for(32))) return fail(ASM_E_INVALID, "symbolic analysis failed");
     std::vector<double> W(S.nnzL, 0.0), d0(S.N), invd;
     for (int64_t q = 0; q < nnz; ++q) W[S.kmap[q]] = vals[q];
     for (int j = 0; j < n_cols; ++j) d0[S.inv[j]] = -dx[j];

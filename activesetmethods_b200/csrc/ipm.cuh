@@ -75,9 +75,13 @@ struct KktDev {
     const int *ws_beg, *ws_end, *wmstep;
     const KktRange *wmchunk;
     const KktBwdItem *bwd;
-    const int *bstep;
+    const int *bs_beg, *bs_end, *bmstep;
+    const KktRange *bmchunk;
+    const KktPanel *panels;
+    const KktPanelTask *ptasks;
     const int *perm, *inv, *kmap;
     double *W, *invd, *diag0;
+    double *PB;   // factorised diagonal blocks of the supernodes (KktPanel::off)
     int nnzL, N;
 };
 
@@ -120,6 +124,64 @@ __device__ __forceinline__ void ldl_apply(const KktDev &d, int tflag, double acc
     } else {
         d.W[(int64_t)t * B + s] -= acc;
     }
+}
+// sum of the terms [q0, q1) of one chunk in ascending order, four terms in flight (with supernodes a chunk holds up to
+// kSnMax terms per source supernode: without the unrolling every term would cost a dependent index -> operand round trip)
+__device__ __forceinline__ double chunk_sum(const KktDev &d, int q0, int q1, int B, int s, int &tflag, double &tv) {
+    KktTerm u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = d.terms[q0 + i < q1 ? q0 + i : q0];
+    tflag = u[0].t;
+    {   // the target travels with the first operands
+        const int t = tflag & ~kLastBit;
+        tv = t >= d.nnzL ? d.diag0[(int64_t)(t - d.nnzL) * B + s] : d.W[(int64_t)t * B + s];
+    }
+    double acc = 0.0;
+    for (int q = q0; q < q1; q += 4) {
+        double a[4], b[4], c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = d.W[(int64_t)u[i].a * B + s];
+            b[i] = d.W[(int64_t)u[i].b * B + s];
+            c[i] = d.invd[(int64_t)u[i].k * B + s];
+        }
+        const int qn = q + 4;
+        if (qn < q1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = d.terms[qn + i < q1 ? qn + i : qn];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (q + i < q1) acc += a[i] * b[i] * c[i];
+    }
+    return acc;
+}
+template <class Item>
+__device__ __forceinline__ double chunk_sum_vec(const KktDev &d, const Item *items, const double *v, int q0, int q1, int B, int s, int &dst, double &tv) {
+    Item u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = items[q0 + i < q1 ? q0 + i : q0];
+    dst = u[0].dst;
+    tv = v[(int64_t)dst * B + s];
+    double acc = 0.0;
+    for (int q = q0; q < q1; q += 4) {
+        double a[4], x[4], c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = d.W[(int64_t)u[i].pos * B + s];
+            x[i] = v[(int64_t)u[i].src * B + s];
+            c[i] = d.invd[(int64_t)u[i].k * B + s];
+        }
+        const int qn = q + 4;
+        if (qn < q1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = items[qn + i < q1 ? qn + i : qn];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (q + i < q1) acc += a[i] * x[i] * c[i];
+    }
+    return acc;
 }
 template <bool BATCH, bool FUSED>
 __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 4) k_ldl_factor(KktDev d, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
@@ -178,14 +240,20 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 
             const int c0 = FUSED ? d.fmstep[l] : rg.m0, c1 = FUSED ? d.fmstep[l + 1] : rg.m1;
             for (int c = c0 + first; c < c1; c += stride) {
                 const KktRange r = d.fmchunk[c];
-                KktTerm u = d.terms[r.begin];
-                const int tflag = u.t;
-                double acc = d.W[(int64_t)u.a * B + s] * d.W[(int64_t)u.b * B + s] * d.invd[(int64_t)u.k * B + s];
-                for (int q = r.begin + 1; q < r.end; ++q) {
-                    u = d.terms[q];
-                    acc += d.W[(int64_t)u.a * B + s] * d.W[(int64_t)u.b * B + s] * d.invd[(int64_t)u.k * B + s];
+                int tflag;
+                double tv;
+                const double acc = chunk_sum(d, r.begin, r.end, B, s, tflag, tv);
+                if (live) {
+                    const int t = tflag & ~kLastBit;
+                    const double r2 = tv - acc;
+                    if (t >= d.nnzL) {
+                        const int64_t e = (int64_t)(t - d.nnzL) * B + s;
+                        d.diag0[e] = r2;
+                        if (tflag & kLastBit) d.invd[e] = 1.0 / r2;
+                    } else {
+                        d.W[(int64_t)t * B + s] = r2;
+                    }
                 }
-                if (live) ldl_apply(d, tflag, acc, B, s);
             }
         }
         if (FUSED) __syncthreads();
@@ -244,14 +312,10 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 
             const int c0 = FUSED ? d.wmstep[l] : rg.m0, c1 = FUSED ? d.wmstep[l + 1] : rg.m1;
             for (int c = c0 + first; c < c1; c += stride) {
                 const KktRange r = d.wmchunk[c];
-                KktFwdItem u = d.fwd[r.begin];
-                const int dst = u.dst;
-                double acc = d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s] * d.invd[(int64_t)u.k * B + s];
-                for (int q = r.begin + 1; q < r.end; ++q) {
-                    u = d.fwd[q];
-                    acc += d.W[(int64_t)u.pos * B + s] * v[(int64_t)u.src * B + s] * d.invd[(int64_t)u.k * B + s];
-                }
-                if (live) v[(int64_t)dst * B + s] -= acc;
+                int dst;
+                double tv;
+                const double acc = chunk_sum_vec(d, d.fwd, v, r.begin, r.end, B, s, dst, tv);
+                if (live) v[(int64_t)dst * B + s] = tv - acc;
             }
         }
         if (FUSED) __syncthreads();
@@ -264,8 +328,9 @@ __global__ void __launch_bounds__(kThreads) k_ldl_diag(KktDev d, double *v, int 
     if (st[mp.s].status >= 0) return;
     for (int64_t k = mp.first; k < d.N; k += mp.stride) v[(int64_t)d.perm[k] * B + mp.s] *= d.invd[k * B + mp.s];
 }
-// backward substitution  v <- L'^-1 v : the rows of a column are its ancestors in the elimination tree and sit on
-// distinct levels, so every item of a step has its own target; steps are walked downwards
+// backward substitution  v <- L'^-1 v : the rows of a column are its ancestors in the elimination tree; without
+// supernodes they sit on distinct levels and every item of a step has its own target, with supernodes a column can have
+// several rows in one step (a chunk).  Steps are walked downwards
 template <bool BATCH, bool FUSED>
 __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 4) k_ldl_bwd(KktDev d, double *v, int B, int l0, int l1, const ScenState *st, KktStepRange rg) {
     pdl_trigger();
@@ -276,7 +341,7 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 
     const int first = BATCH ? blockIdx.x * bw + warp : blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = BATCH ? gridDim.x * bw : gridDim.x * blockDim.x;
     for (int l = l1 - 1; l >= l0; --l) {
-        const int q0 = FUSED ? d.bstep[l] : rg.s0, q1 = FUSED ? d.bstep[l + 1] : rg.s1;
+        const int q0 = FUSED ? d.bs_beg[l] : rg.s0, q1 = FUSED ? d.bs_end[l] : rg.s1;
         {   // loads are never gated on the scenario's status (it would put one more dependent load on the critical path); stores are
             if (BATCH) {
                 int q = q0 + 4 * first;
@@ -314,8 +379,330 @@ __global__ void __launch_bounds__(FUSED ? kFusedThreads : kThreads, FUSED ? 1 : 
                     if (live) v[u.dst] -= d.invd[u.k] * d.W[u.pos] * v[u.src];
                 }
             }
+            const int c0 = FUSED ? d.bmstep[l] : rg.m0, c1 = FUSED ? d.bmstep[l + 1] : rg.m1;
+            for (int c = c0 + first; c < c1; c += stride) {
+                const KktRange r = d.bmchunk[c];
+                int dst;
+                double tv;
+                const double acc = chunk_sum_vec(d, d.bwd, v, r.begin, r.end, B, s, dst, tv);
+                if (live) v[(int64_t)dst * B + s] = tv - acc;
+            }
         }
         if (FUSED) __syncthreads();
+    }
+}
+
+// =================================== supernode panels ===========================================================
+// A supernode = w <= kSnMax columns c_0 < ... < c_w-1 with nested patterns: a dense w x w diagonal block and nr dense
+// rows below it ("panel").  At the start of its step every update from outside has been applied.  The diagonal block is
+// factorised right-looking (W = L D convention, as everywhere); its strictly lower part goes, scaled to L = W / d, to
+// a buffer of its own (PB, KktPanel::off) that the rows and the substitutions read.  Then every row below is solved:
+//     w[t,k] final  ->  w[t,i] -= w[t,k] * L[i,k]  for i > k        (right-looking: the dependent chain is w long)
+// rows are independent of each other and every entry of the panel is read and written once.  Lanes are scenarios, as
+// in the step kernels (a single LP runs the same kernels on one lane: the panels are a small part of its work).
+//   k_sn_diag : panels wider than kSnSmall -- a block per (panel, 32 scenarios), diagonal block in shared memory;
+//               narrow panels (most: separators of two or three buses) -- a warp per task, block AND rows, in registers
+//   k_sn_rows : the rows of the wide panels, a block per kPanelRowsWide rows, a warp per row
+//   k_sn_solve: the supernode's part of a substitution, a warp per panel
+// Block-cooperative fetches use cp.async: a loop of load -> shared store would serialise one L2 round trip per entry.
+__device__ __forceinline__ int sn_tri(int j, int i) { return j * (j + 1) / 2 + i; }   // j >= i
+constexpr int kSnTri = kSnMax * (kSnMax + 1) / 2;
+constexpr int kPanelThreads = 256;
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__global__ void __launch_bounds__(kPanelThreads, 2) k_sn_diag(KktDev d, int B, int p0, int nwide, int t0n, int nnarrow, const ScenState *st) {
+    pdl_trigger();
+    __shared__ double S[kSnTri][32];
+    __shared__ double Iv[kSnMax][32];
+    __shared__ int pc[kSnMax], pl[kSnMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nw = kPanelThreads / 32;
+    const int s = min((int)blockIdx.y * 32 + lane, B - 1);   // single LP (B == 1): lane 0 works, the others shadow it
+    const bool live = (int)blockIdx.y * 32 + lane < B && st[s].status < 0;
+    if ((int)blockIdx.x >= nwide) {   // ---- narrow panels: block and rows
+        const int ti = ((int)blockIdx.x - nwide) * nw + warp;
+        if (ti >= nnarrow) return;
+        const KktPanelTask task = d.ptasks[t0n + ti];
+        const KktPanel *P = d.panels + task.panel;
+        const int w = P->w, nr = P->nr;
+        int c[kSnSmall], lp[kSnSmall];
+#pragma unroll
+        for (int i = 0; i < kSnSmall; ++i) {
+            c[i] = P->col[i];
+            lp[i] = P->lp[i];
+        }
+        pdl_wait();
+        double A[kSnSmall][kSnSmall], iv[kSnSmall];
+#pragma unroll
+        for (int j = 0; j < kSnSmall; ++j)
+#pragma unroll
+            for (int i = 0; i <= j; ++i)
+                if (j < w) A[j][i] = i == j ? d.diag0[(int64_t)c[j] * B + s] : d.W[(int64_t)(lp[i] + j - i - 1) * B + s];
+        const int t1 = min(task.r0 + kPanelRows, nr);
+        double a[4][kSnSmall];   // the first four rows travel with the block
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < kSnSmall; ++i)
+                if (i < w && t1 > task.r0) a[r][i] = d.W[(int64_t)(lp[i] + w - 1 - i + min(task.r0 + r, t1 - 1)) * B + s];
+#pragma unroll
+        for (int i = 0; i < kSnSmall; ++i) {
+            if (i < w) {
+                iv[i] = 1.0 / A[i][i];
+#pragma unroll
+                for (int k = i + 1; k < kSnSmall; ++k) {
+                    if (k < w) {
+                        const double f = A[k][i] * iv[i];
+#pragma unroll
+                        for (int j = k; j < kSnSmall; ++j)
+                            if (j < w) A[j][k] -= A[j][i] * f;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 1; j < kSnSmall; ++j)   // L = W / d
+#pragma unroll
+            for (int i = 0; i < j; ++i)
+                if (j < w) A[j][i] *= iv[i];
+        if (task.r0 == 0 && live) {
+            const int64_t off = P->off;
+#pragma unroll
+            for (int j = 0; j < kSnSmall; ++j) {
+                if (j < w) {
+                    d.invd[(int64_t)c[j] * B + s] = iv[j];
+#pragma unroll
+                    for (int i = 0; i < j; ++i) d.PB[(off + sn_tri(j, i)) * B + s] = A[j][i];
+                }
+            }
+        }
+        for (int t = task.r0; t < t1; t += 4) {   // four rows in flight
+            if (t > task.r0) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int i = 0; i < kSnSmall; ++i)
+                        if (i < w) a[r][i] = d.W[(int64_t)(lp[i] + w - 1 - i + min(t + r, t1 - 1)) * B + s];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (t + r < t1) {
+#pragma unroll
+                    for (int k = 0; k < kSnSmall; ++k) {
+                        if (k < w) {
+                            if (k > 0 && live) d.W[(int64_t)(lp[k] + w - 1 - k + t + r) * B + s] = a[r][k];
+#pragma unroll
+                            for (int i = k + 1; i < kSnSmall; ++i)
+                                if (i < w) a[r][i] -= a[r][k] * A[i][k];
+                        }
+                    }
+                }
+            }
+        }
+        return;
+    }
+    // ---- wide panels: the diagonal block
+    const KktPanel *P = d.panels + p0 + blockIdx.x;
+    const int w = P->w;
+    if (threadIdx.x < kSnMax) {
+        pc[threadIdx.x] = P->col[threadIdx.x];
+        pl[threadIdx.x] = P->lp[threadIdx.x];
+    }
+    __syncthreads();
+    pdl_wait();
+    {   // entries e = warp, warp + nw, ... of the packed lower triangle
+        int j = 0, i = warp;
+        while (i > j) i -= ++j;
+        while (j < w) {
+            cp_async8(&S[sn_tri(j, i)][lane], i == j ? d.diag0 + (int64_t)pc[j] * B + s : d.W + (int64_t)(pl[i] + j - i - 1) * B + s);
+            i += nw;
+            while (i > j) i -= ++j;
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+    for (int i = 0; i < w; ++i) {
+        const double iv = 1.0 / S[sn_tri(i, i)][lane];
+        if (warp == 0) Iv[i][lane] = iv;
+        // rows i+1 .. w-1 of the trailing block, a long and a short one per warp
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int ja = i + 1 + warp, jb = w - 1 - warp;
+            const int j = pass == 0 ? ja : jb;
+            if (pass == 0 ? ja <= jb : jb > ja) {
+                const double g = S[sn_tri(j, i)][lane] * iv;
+#pragma unroll 4
+                for (int k = i + 1; k <= j; ++k) S[sn_tri(j, k)][lane] -= g * S[sn_tri(k, i)][lane];
+            }
+        }
+        __syncthreads();
+    }
+    if (live) {
+        const int64_t off = P->off;
+        int j = 0, i = warp;
+        while (i > j) i -= ++j;
+        while (j < w) {
+            if (i == j)
+                d.invd[(int64_t)pc[j] * B + s] = Iv[j][lane];
+            else
+                d.PB[(off + sn_tri(j, i)) * B + s] = S[sn_tri(j, i)][lane] * Iv[i][lane];
+            i += nw;
+            while (i > j) i -= ++j;
+        }
+    }
+}
+__global__ void __launch_bounds__(kPanelThreads, 2) k_sn_rows(KktDev d, int B, int t0, const ScenState *st) {
+    pdl_trigger();
+    __shared__ double L[kSnTri][32];
+    __shared__ int pl[kSnMax];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nw = kPanelThreads / 32;
+    const int s = min((int)blockIdx.y * 32 + lane, B - 1);   // single LP (B == 1): lane 0 works, the others shadow it
+    const bool live = (int)blockIdx.y * 32 + lane < B && st[s].status < 0;
+    const KktPanelTask task = d.ptasks[t0 + blockIdx.x];
+    const KktPanel *P = d.panels + task.panel;
+    const int w = P->w, nr = P->nr;
+    const int64_t off = P->off;
+    if (threadIdx.x < kSnMax) pl[threadIdx.x] = P->lp[threadIdx.x];
+    __syncthreads();
+    pdl_wait();
+    {   // strictly lower entries of the factorised block
+        int j = 1, i = warp;
+        while (i >= j) i -= j++;
+        while (j < w) {
+            cp_async8(&L[sn_tri(j, i)][lane], d.PB + (off + sn_tri(j, i)) * B + s);
+            i += nw;
+            while (i >= j) i -= j++;
+        }
+    }
+    const int t1 = min(task.r0 + kPanelRowsWide, nr);
+    const int t = task.r0 + warp;   // kPanelRowsWide == 2 * nw: two rows per warp
+    double a[2][kSnMax];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < kSnMax; ++i)
+            if (i < w) a[r][i] = d.W[(int64_t)(pl[i] + w - 1 - i + min(t + r * nw, nr - 1)) * B + s];
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSnMax; ++k) {
+        if (k < w) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (k > 0 && live && t + r * nw < t1) d.W[(int64_t)(pl[k] + w - 1 - k + t + r * nw) * B + s] = a[r][k];
+            }
+#pragma unroll
+            for (int i = k + 1; i < kSnMax; ++i) {
+                if (i < w) {
+                    const double l = L[sn_tri(i, k)][lane];
+                    a[0][i] -= a[0][k] * l;
+                    a[1][i] -= a[1][k] * l;
+                }
+            }
+        }
+    }
+}
+// the supernode's part of a substitution: v_S <- L_SS^-1 v_S (FWD, before the step's fan-out) or L_SS'^-1 v_S (after
+// the contributions of the higher steps, before the fan-out to the descendants).  Wide panels: a block per panel, the
+// factorised block goes to shared memory in one asynchronous sweep, the first warp walks it (w dependent steps);
+// narrow panels: a warp each, in registers
+constexpr int kPanelSolveThreads = 128;
+template <bool FWD>
+__global__ void __launch_bounds__(kPanelSolveThreads) k_sn_solve(KktDev d, double *v, int B, int p0, int nwide, int npanels, const ScenState *st) {
+    pdl_trigger();
+    __shared__ double S[kSnTri][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int nw = kPanelSolveThreads / 32;
+    const int s = min((int)blockIdx.y * 32 + lane, B - 1);   // single LP (B == 1): lane 0 works, the others shadow it
+    const bool live = (int)blockIdx.y * 32 + lane < B && st[s].status < 0;
+    if ((int)blockIdx.x >= nwide) {   // ---- narrow panels
+        const int pi = nwide + ((int)blockIdx.x - nwide) * nw + warp;
+        if (pi >= npanels) return;
+        const KktPanel *P = d.panels + p0 + pi;
+        const int w = P->w;
+        const int64_t off = P->off;
+        int nd[kSnSmall];
+#pragma unroll
+        for (int i = 0; i < kSnSmall; ++i) nd[i] = P->node[i];
+        pdl_wait();
+        double L[kSnSmall][kSnSmall], x[kSnSmall];
+#pragma unroll
+        for (int j = 0; j < kSnSmall; ++j) {
+            if (j < w) {
+                x[j] = v[(int64_t)nd[j] * B + s];
+#pragma unroll
+                for (int i = 0; i < j; ++i) L[j][i] = d.PB[(off + sn_tri(j, i)) * B + s];
+            }
+        }
+        if (FWD) {
+#pragma unroll
+            for (int j = 1; j < kSnSmall; ++j) {
+                if (j < w) {
+#pragma unroll
+                    for (int i = 0; i < j; ++i) x[j] -= L[j][i] * x[i];
+                    if (live) v[(int64_t)nd[j] * B + s] = x[j];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = kSnSmall - 2; i >= 0; --i) {
+                if (i < w - 1) {
+#pragma unroll
+                    for (int j = i + 1; j < kSnSmall; ++j)
+                        if (j < w) x[i] -= L[j][i] * x[j];
+                    if (live) v[(int64_t)nd[i] * B + s] = x[i];
+                }
+            }
+        }
+        return;
+    }
+    // ---- wide panels
+    const KktPanel *P = d.panels + p0 + blockIdx.x;
+    const int w = P->w;
+    const int64_t off = P->off;
+    pdl_wait();
+    {
+        int j = 1, i = warp;
+        while (i >= j) i -= j++;
+        while (j < w) {
+            cp_async8(&S[sn_tri(j, i)][lane], d.PB + (off + sn_tri(j, i)) * B + s);
+            i += nw;
+            while (i >= j) i -= j++;
+        }
+    }
+    double x[kSnMax];
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < kSnMax; ++j)
+            if (j < w) x[j] = v[(int64_t)P->node[j] * B + s];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (warp != 0) return;
+    if (FWD) {
+#pragma unroll
+        for (int i = 0; i < kSnMax; ++i) {
+            if (i < w) {
+                if (i > 0 && live) v[(int64_t)P->node[i] * B + s] = x[i];
+#pragma unroll
+                for (int j = i + 1; j < kSnMax; ++j)
+                    if (j < w) x[j] -= S[sn_tri(j, i)][lane] * x[i];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = kSnMax - 1; j >= 0; --j) {
+            if (j < w) {
+                if (j < w - 1 && live) v[(int64_t)P->node[j] * B + s] = x[j];
+#pragma unroll
+                for (int i = 0; i < j; ++i) x[i] -= S[sn_tri(j, i)][lane] * x[j];
+            }
+        }
     }
 }
 
@@ -979,12 +1366,14 @@ struct IpmEngine {
     KktSymbolic sym;
     bool ready = false;
     int B = 0;
-    DBuf<int> fs_beg, fs_end, fmstep, ws_beg, ws_end, wmstep, bstep, perm, inv, kmap;
-    DBuf<KktRange> fmchunk, wmchunk;
+    DBuf<int> fs_beg, fs_end, fmstep, ws_beg, ws_end, wmstep, bs_beg, bs_end, bmstep, perm, inv, kmap;
+    DBuf<KktRange> fmchunk, wmchunk, bmchunk;
+    DBuf<KktPanel> panels;
+    DBuf<KktPanelTask> ptasks;
     DBuf<KktTerm> terms;
     DBuf<KktFwdItem> fwd;
     DBuf<KktBwdItem> bwd;
-    DBuf<double> W, invd, diag0;
+    DBuf<double> W, invd, diag0, PB;
     DBuf<double> colv[9], rowv[12], kktv[3];
     DBuf<IpmState> ist;
     cudaGraphExec_t g_factor = nullptr, g_solve_sol = nullptr, g_solve_work = nullptr;
@@ -1008,6 +1397,13 @@ struct IpmEngine {
         if (e) return atoi(e);
         return B == 1 ? 2048 : 64;
     }
+    // widest supernode (1 = none)
+    static int supernode_for(int B) {
+        const char *e = getenv(B == 1 ? "ASM_IPM_SUPERNODE_SINGLE" : "ASM_IPM_SUPERNODE");
+        if (e) return std::max(1, std::min(atoi(e), kSnMax));
+        return kSnMax;
+    }
+    bool supernodal() const { return !sym.panels.empty(); }
     template <class T>
     static int up(DBuf<T> &dst, const std::vector<T> &src) {
         ASM_TRY(dst.alloc(std::max<size_t>(src.size(), 1)));
@@ -1024,7 +1420,7 @@ struct IpmEngine {
                 return fail(ASM_E_INVALID, "duplicate (row, column) entries in the pattern: the barrier engine needs a deduplicated CSR");
         }
         const auto t0 = std::chrono::steady_clock::now();
-        if (sym.build(n, m, row_ptr.data(), col_idx.data(), narrow_for(B)))
+        if (sym.build(n, m, row_ptr.data(), col_idx.data(), narrow_for(B), supernode_for(B)))
             return fail(ASM_E_INVALID, "KKT symbolic analysis failed (index out of range or more than 2^31 update terms)");
         symbolic_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         ASM_TRY(up(terms, sym.terms));
@@ -1038,7 +1434,12 @@ struct IpmEngine {
         ASM_TRY(up(wmstep, sym.wmstep));
         ASM_TRY(up(wmchunk, sym.wmchunk));
         ASM_TRY(up(bwd, sym.bwd));
-        ASM_TRY(up(bstep, sym.bstep));
+        ASM_TRY(up(bs_beg, sym.bs_beg));
+        ASM_TRY(up(bs_end, sym.bs_end));
+        ASM_TRY(up(bmstep, sym.bmstep));
+        ASM_TRY(up(bmchunk, sym.bmchunk));
+        ASM_TRY(up(panels, sym.panels));
+        ASM_TRY(up(ptasks, sym.ptasks));
         ASM_TRY(up(perm, sym.perm));
         ASM_TRY(up(inv, sym.inv));
         ASM_TRY(up(kmap, sym.kmap));
@@ -1047,11 +1448,14 @@ struct IpmEngine {
         std::vector<KktFwdItem>().swap(sym.fwd);
         std::vector<KktBwdItem>().swap(sym.bwd);
         std::vector<KktRange>().swap(sym.fmchunk);
+        std::vector<KktRange>().swap(sym.wmchunk);
+        std::vector<KktRange>().swap(sym.bmchunk);
         n_fchunks = sym.n_fchunks;
         const size_t N = sym.N;
         ASM_TRY(W.alloc(std::max<size_t>(sym.nnzL, 1) * B));
         ASM_TRY(invd.alloc(N * B));
         ASM_TRY(diag0.alloc(N * B));
+        ASM_TRY(PB.alloc(std::max<size_t>(sym.panel_slots, 1) * B));
         for (auto &b : colv) ASM_TRY(b.alloc((size_t)n * B));
         for (auto &b : rowv) ASM_TRY(b.alloc((size_t)std::max(m, 1) * B));
         for (auto &b : kktv) ASM_TRY(b.alloc(N * B));
@@ -1073,13 +1477,19 @@ struct IpmEngine {
         d.wmstep = wmstep.p;
         d.wmchunk = wmchunk.p;
         d.bwd = bwd.p;
-        d.bstep = bstep.p;
+        d.bs_beg = bs_beg.p;
+        d.bs_end = bs_end.p;
+        d.bmstep = bmstep.p;
+        d.bmchunk = bmchunk.p;
+        d.panels = panels.p;
+        d.ptasks = ptasks.p;
         d.perm = perm.p;
         d.inv = inv.p;
         d.kmap = kmap.p;
         d.W = W.p;
         d.invd = invd.p;
         d.diag0 = diag0.p;
+        d.PB = PB.p;
         d.nnzL = (int)sym.nnzL;
         d.N = sym.N;
         return d;
@@ -1121,13 +1531,14 @@ struct IpmEngine {
         cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
     }
     // grid of a step kernel.  Batch: a warp per item, scenarios over blockIdx.y; single LP: a thread per item
-    dim3 level_grid(const KktLaunch &L) const {
+    dim3 level_grid(const KktLaunch &L, int64_t multi = 0) const {
         unsigned gx = 1;
         const int per_block = B == 1 ? kThreads : kWarps;
         if (!L.fused) {
             const int gy = B == 1 ? 1 : B / 32;
             int64_t cap = std::max<int64_t>(1, (int64_t)kMaxBlocksX * 4 / gy);
-            const int64_t units = B == 1 ? L.items : (L.items + 3) / 4 + 1;   // batch: four single-term chunks per warp pass
+            // batch: four single-term chunks per warp pass, one multi-term chunk per warp pass
+            const int64_t units = B == 1 ? L.items : (L.items - multi + 3) / 4 + multi + 1;
             gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((units + per_block - 1) / per_block, cap));
         }
         return dim3(gx, B == 1 ? 1 : B / 32);
@@ -1144,6 +1555,35 @@ struct IpmEngine {
                 k_kkt_scatter<false><<<gz.grid, gz.block, 0, st>>>(v, d, nz);
         }
         count += 2;
+        if (supernodal()) {   // per step: the panels of its supernodes, then the updates that leave them
+            const int gy = (B + 31) / 32;
+            for (int l = 0; l < sym.n_levels; ++l) {
+                // wide tasks (rows of the wide panels) come first in the step's task range, then the narrow tasks
+                const int np = sym.pstep[l + 1] - sym.pstep[l], npw = sym.pwide[l];
+                const int nt = sym.ptstep[l + 1] - sym.ptstep[l], ntw = sym.ptwide[l];
+                if (np > 0) {
+                    const int per = kPanelThreads / 32;
+                    launch_step(k_sn_diag, dim3(npw + (nt - ntw + per - 1) / per, gy), kPanelThreads, st, d, B, sym.pstep[l], npw,
+                                sym.ptstep[l] + ntw, nt - ntw, v.state);
+                    ++count;
+                }
+                if (ntw > 0) {
+                    launch_step(k_sn_rows, dim3(ntw, gy), kPanelThreads, st, d, B, sym.ptstep[l], v.state);
+                    ++count;
+                }
+                const KktStepRange rg = {sym.fs_beg[l], sym.fs_end[l], sym.fmstep[l], sym.fmstep[l + 1]};
+                const int multi = rg.m1 - rg.m0, items = rg.s1 - rg.s0 + multi;
+                if (items > 0) {
+                    const dim3 grid = level_grid(KktLaunch{l, l + 1, 0, items}, multi);
+                    if (B > 1)
+                        launch_step(k_ldl_factor<true, false>, grid, kThreads, st, d, B, l, l + 1, v.state, rg);
+                    else
+                        launch_step(k_ldl_factor<false, false>, grid, kThreads, st, d, B, l, l + 1, v.state, rg);
+                    ++count;
+                }
+            }
+            return;
+        }
         for (const KktLaunch &L : sym.flaunch) {
             const dim3 grid = level_grid(L);
             const KktStepRange rg = {sym.fs_beg[L.l0], sym.fs_end[L.l0], sym.fmstep[L.l0], sym.fmstep[L.l0 + 1]};
@@ -1163,6 +1603,52 @@ struct IpmEngine {
     }
     void enqueue_solve(LpView &v, double *vec, cudaStream_t st, int64_t &count) {
         KktDev d = dev();
+        if (supernodal()) {
+            const int gy = (B + 31) / 32;
+            for (int l = 0; l < sym.n_levels; ++l) {
+                const int np = sym.pstep[l + 1] - sym.pstep[l], nwide = sym.pwide[l];
+                if (np > 0) {
+                    const int per = kPanelSolveThreads / 32;
+                    launch_step(k_sn_solve<true>, dim3(nwide + (np - nwide + per - 1) / per, gy), kPanelSolveThreads, st, d, vec, B, sym.pstep[l], nwide, np, v.state);
+                    ++count;
+                }
+                const KktStepRange rg = {sym.ws_beg[l], sym.ws_end[l], sym.wmstep[l], sym.wmstep[l + 1]};
+                const int multi = rg.m1 - rg.m0, items = rg.s1 - rg.s0 + multi;
+                if (items > 0) {
+                    const dim3 grid = level_grid(KktLaunch{l, l + 1, 0, items}, multi);
+                    if (B > 1)
+                        launch_step(k_ldl_fwd<true, false>, grid, kThreads, st, d, vec, B, l, l + 1, v.state, rg);
+                    else
+                        launch_step(k_ldl_fwd<false, false>, grid, kThreads, st, d, vec, B, l, l + 1, v.state, rg);
+                    ++count;
+                }
+            }
+            const Geo gN = geo_for(sym.N, B);
+            if (B > 1)
+                k_ldl_diag<true><<<gN.grid, gN.block, 0, st>>>(d, vec, B, v.state);
+            else
+                k_ldl_diag<false><<<gN.grid, gN.block, 0, st>>>(d, vec, B, v.state);
+            ++count;
+            for (int l = sym.n_levels - 1; l >= 0; --l) {
+                const int np = sym.pstep[l + 1] - sym.pstep[l], nwide = sym.pwide[l];
+                if (np > 0) {
+                    const int per = kPanelSolveThreads / 32;
+                    launch_step(k_sn_solve<false>, dim3(nwide + (np - nwide + per - 1) / per, gy), kPanelSolveThreads, st, d, vec, B, sym.pstep[l], nwide, np, v.state);
+                    ++count;
+                }
+                const KktStepRange rg = {sym.bs_beg[l], sym.bs_end[l], sym.bmstep[l], sym.bmstep[l + 1]};
+                const int multi = rg.m1 - rg.m0, items = rg.s1 - rg.s0 + multi;
+                if (items > 0) {
+                    const dim3 grid = level_grid(KktLaunch{l, l + 1, 0, items}, multi);
+                    if (B > 1)
+                        launch_step(k_ldl_bwd<true, false>, grid, kThreads, st, d, vec, B, l, l + 1, v.state, rg);
+                    else
+                        launch_step(k_ldl_bwd<false, false>, grid, kThreads, st, d, vec, B, l, l + 1, v.state, rg);
+                    ++count;
+                }
+            }
+            return;
+        }
         for (const KktLaunch &L : sym.wlaunch) {
             const dim3 grid = level_grid(L);
             const KktStepRange rg = {sym.ws_beg[L.l0], sym.ws_end[L.l0], sym.wmstep[L.l0], sym.wmstep[L.l0 + 1]};
@@ -1190,7 +1676,7 @@ struct IpmEngine {
         for (auto it = sym.blaunch.rbegin(); it != sym.blaunch.rend(); ++it) {
             const KktLaunch &L = *it;
             const dim3 grid = level_grid(L);
-            const KktStepRange rg = {sym.bstep[L.l0], sym.bstep[L.l0 + 1], 0, 0};
+            const KktStepRange rg = {sym.bs_beg[L.l0], sym.bs_end[L.l0], sym.bmstep[L.l0], sym.bmstep[L.l0 + 1]};
             if (B > 1) {
                 if (L.fused)
                     launch_step(k_ldl_bwd<true, true>, grid, kFusedThreads, st, d, vec, B, L.l0, L.l1, v.state, rg);

@@ -22,7 +22,14 @@
 //   * the same chunked fan-out lists for the forward substitution; the backward substitution needs no chunks
 //     (the rows of a column are its ancestors, which sit on distinct levels),
 //   * the launch plan (wide steps: one launch each; runs of narrow steps: one launch of a single block per 32
-//     scenarios that walks them with __syncthreads()).
+//     scenarios that walks them with __syncthreads()),
+//   * optionally (sn > 1) SUPERNODES: chains c_0 -> c_1 -> ... of at most sn columns along the elimination tree whose
+//     patterns nest exactly (pattern(c_i) = {c_i+1} + pattern(c_i+1)), the separators of the network.  All columns
+//     of a supernode share one step; the updates inside a supernode (its dense diagonal block and the rows below
+//     it, "panel") are taken out of the term lists and done by a dense panel kernel at the start of the step, the
+//     updates that leave it stay in the lists -- now one chunk of up to sn terms per target and step instead of
+//     sn single-term read-modify-writes on sn steps.  A 1354-bus KKT matrix goes from 310 levels to 49 steps and
+//     from 2.47 M to 0.47 M target updates per factorisation.
 // No CUDA in this header: it is also compiled into the host-only self test (asm_kkt_selftest).
 #pragma once
 #include <stdint.h>
@@ -52,6 +59,20 @@ struct KktLaunch {
     int items;   // largest step of the launch
 };
 constexpr int kLastBit = 1 << 30;  // in KktTerm::t of the first term of a chunk: last update of this pivot -> invert it
+constexpr int kSnMax = 16;         // widest supernode
+constexpr int kSnSmall = 4;        // panels up to this width are factorised by one warp per task, wider ones by a block
+constexpr int kPanelRows = 32;     // rows of a narrow panel one task (warp) solves
+constexpr int kPanelRowsWide = 16; // rows of a wide panel one task (block) solves
+struct KktPanel {                  // a supernode of 2..kSnMax columns c_0 < c_1 < ... (permuted numbering)
+    int w, nr;                     // columns; rows below the diagonal block (= pattern of the last column)
+    int off;                       // first of its w (w + 1) / 2 slots in the buffer of factorised diagonal blocks
+    int col[kSnMax];
+    int node[kSnMax];              // perm[col[i]]: where the right-hand side entry of column i lives
+    int lp[kSnMax];                // Lp[c_i]: entry (c_j, c_i), j > i, is lp[i] + j-i-1; entry (row t below, c_i) is lp[i] + w-1-i + t
+};
+struct KktPanelTask {
+    int panel, r0;                 // rows [r0, r0 + kPanelRows(Wide)) of the panel
+};
 
 struct KktSymbolic {
     int n = 0, m = 0, N = 0;
@@ -77,13 +98,27 @@ struct KktSymbolic {
     std::vector<KktFwdItem> fwd;
     std::vector<int> ws_beg, ws_end, wmstep;
     std::vector<KktRange> wmchunk;
-    // backward substitution: items of step l = entries whose row has level l (walked downwards)
+    // backward substitution: items of step l = entries whose row has level l (walked downwards); with supernodes a
+    // column can have several rows on one step, hence the same singles / chunks layout
     std::vector<KktBwdItem> bwd;
-    std::vector<int> bstep;
+    std::vector<int> bs_beg, bs_end, bmstep;
+    std::vector<KktRange> bmchunk;
     std::vector<KktLaunch> flaunch, wlaunch, blaunch;
+    // supernodes (empty when built with sn <= 1): panels sorted by step, pstep[l] .. pstep[l+1]; the row tasks of the
+    // factorisation likewise in ptstep
+    int sn_width = 1;
+    std::vector<int> snid;         // per permuted column
+    std::vector<KktPanel> panels;
+    std::vector<int> pstep, ptstep;
+    std::vector<int> ptwide, pwide;   // per step: how many of its tasks / panels are wider than kSnSmall (they come first)
+    std::vector<KktPanelTask> ptasks;
+    int64_t n_intra = 0;           // update terms that the panels absorb
+    int64_t panel_slots = 0;       // size of the buffer of factorised diagonal blocks (entries per LP)
 
     // K: m x n CSR pattern (0-based).  Returns 0, or -1 when an index is out of range / the term count overflows.
-    int build(int n_, int m_, const int *row_ptr, const int *col_idx, int narrow = 64) {
+    int build(int n_, int m_, const int *row_ptr, const int *col_idx, int narrow = 64, int sn = 1) {
+        sn_width = std::max(1, std::min(sn, kSnMax));
+        n_intra = 0;
         n = n_;
         m = m_;
         N = n + m;
@@ -176,8 +211,19 @@ struct KktSymbolic {
         level.assign(N, 0);
         for (int k = 0; k < N; ++k)
             for (int p = Lp[k]; p < Lp[k + 1]; ++p) level[Li[p]] = std::max(level[Li[p]], level[k] + 1);
+        snid.resize(N);
+        for (int k = 0; k < N; ++k) snid[k] = k;
+        panels.clear();
+        if (sn_width > 1) supernodes();
         n_levels = 0;
         for (int k = 0; k < N; ++k) n_levels = std::max(n_levels, level[k] + 1);
+        if (panels.empty()) {
+            pstep.assign(n_levels + 1, 0);
+            ptstep.assign(n_levels + 1, 0);
+            ptwide.assign(n_levels, 0);
+            pwide.assign(n_levels, 0);
+            ptasks.clear();
+        }
         // ---- terms, target-major first (column k updates entry (r_a, r_b) and pivot r_b for every pair of its rows
         //      r_a >= r_b), then a stable counting sort by the level of k: (level, target, k) order
         const int64_t n_targets = nnzL + N;
@@ -189,6 +235,10 @@ struct KktSymbolic {
                     const int p0 = Lp[k], p1 = Lp[k + 1];
                     for (int pb = p0; pb < p1; ++pb) {
                         const int j = Li[pb];
+                        if (snid[j] == snid[k]) {   // target column in the supernode of k: the panel kernel's work
+                            if (pass == 0) n_intra += p1 - pb;
+                            continue;
+                        }
                         const int64_t td = nnzL + j;
                         if (pass == 0)
                             ++cnt[td + 1];
@@ -244,24 +294,31 @@ struct KktSymbolic {
             for (int k = 0; k < N; ++k)
                 for (int p = Lp[k]; p < Lp[k + 1]; ++p) rl[pos[Li[p]]++] = KktFwdItem{p, perm[k], k, perm[Li[p]]};
             std::vector<int64_t> lpos(n_levels + 1, 0);
-            for (const KktFwdItem &u : rl) ++lpos[level[u.k] + 1];
+            int64_t kept = 0;
+            for (const KktFwdItem &u : rl)
+                if (snid[inv[u.dst]] != snid[u.k]) ++lpos[level[u.k] + 1], ++kept;
             for (int l = 0; l < n_levels; ++l) lpos[l + 1] += lpos[l];
-            fwd.resize(nnzL);
-            for (const KktFwdItem &u : rl) fwd[lpos[level[u.k]]++] = u;
+            fwd.resize(kept);
+            for (const KktFwdItem &u : rl)
+                if (snid[inv[u.dst]] != snid[u.k]) fwd[lpos[level[u.k]]++] = u;
         }
         n_wchunks = regroup(fwd, [&](const KktFwdItem &u) { return level[u.k]; }, [](const KktFwdItem &u) { return u.dst; },
                             ws_beg, ws_end, wmstep, wmchunk);
         // ---- backward substitution: entry (i, j) is applied when x_i is final, i.e. at the level of its row
-        {
-            bstep.assign(n_levels + 1, 0);
-            for (int64_t p = 0; p < nnzL; ++p) ++bstep[level[Li[p]] + 1];
-            for (int l = 0; l < n_levels; ++l) bstep[l + 1] += bstep[l];
-            bwd.resize(nnzL);
-            std::vector<int> pos(bstep.begin(), bstep.end() - 1);
+        {   // items of one (step, column) are contiguous: k ascending, p ascending
+            std::vector<int64_t> bstep(n_levels + 1, 0);
             for (int k = 0; k < N; ++k)
                 for (int p = Lp[k]; p < Lp[k + 1]; ++p)
-                    bwd[pos[level[Li[p]]]++] = KktBwdItem{p, perm[Li[p]], perm[k], k};
+                    if (snid[Li[p]] != snid[k]) ++bstep[level[Li[p]] + 1];
+            for (int l = 0; l < n_levels; ++l) bstep[l + 1] += bstep[l];
+            bwd.resize(bstep[n_levels]);
+            std::vector<int64_t> pos(bstep.begin(), bstep.end() - 1);
+            for (int k = 0; k < N; ++k)
+                for (int p = Lp[k]; p < Lp[k + 1]; ++p)
+                    if (snid[Li[p]] != snid[k]) bwd[pos[level[Li[p]]]++] = KktBwdItem{p, perm[Li[p]], perm[k], k};
         }
+        regroup(bwd, [&](const KktBwdItem &u) { return level[inv[u.src]]; }, [](const KktBwdItem &u) { return u.dst; },
+                bs_beg, bs_end, bmstep, bmchunk);
         auto work = [&](const std::vector<int> &sb, const std::vector<int> &se, const std::vector<int> &ms) {
             std::vector<int> w(n_levels + 1, 0);
             for (int l = 0; l < n_levels; ++l) w[l + 1] = w[l] + (se[l] - sb[l]) + (ms[l + 1] - ms[l]);
@@ -291,18 +348,117 @@ struct KktSymbolic {
                 }
             std::fill(stampV.begin(), stampV.end(), -1);
             std::fill(stampDst.begin(), stampDst.end(), -1);
+            q = 0;
             for (int l = 0; l < n_levels; ++l)
-                for (int p = bstep[l]; p < bstep[l + 1]; ++p) {
-                    const KktBwdItem &u = bwd[p];
+                for (; q < bwd.size() && level[inv[bwd[q].src]] == l; ++q) {
+                    const KktBwdItem &u = bwd[q];
                     ++b_distinct_reads;
                     if (stampV[u.src] != l) { stampV[u.src] = l; ++b_distinct_reads; }
                     if (stampDst[u.dst] != l) { stampDst[u.dst] = l; b_distinct_reads += 1; ++b_targets; }   // 1/d[dst]
                 }
+            // panels: every entry of a panel is read and written once by the factorisation (the diagonal block once
+            // more per row task) and read once by each substitution; the right-hand side entries are targets
+            for (const KktPanel &P : panels) {
+                const int64_t tri = (int64_t)P.w * (P.w - 1) / 2;
+                const bool wide = P.w > kSnSmall;
+                const int64_t tasks = wide ? (P.nr + kPanelRowsWide - 1) / kPanelRowsWide : std::max(1, (P.nr + kPanelRows - 1) / kPanelRows);
+                f_targets += tri + P.w + (int64_t)P.nr * (P.w - 1);
+                f_distinct_reads += (wide ? tasks * tri : (tasks - 1) * (tri + P.w)) + P.nr;
+                w_distinct_reads += tri + P.w;
+                w_targets += P.w;
+                b_distinct_reads += tri + P.w;
+                b_targets += P.w;
+            }
         }
         plan(work(fs_beg, fs_end, fmstep), narrow, flaunch);
         plan(work(ws_beg, ws_end, wmstep), narrow, wlaunch);
-        plan(bstep, narrow, blaunch);
+        plan(work(bs_beg, bs_end, bmstep), narrow, blaunch);
         return 0;
+    }
+
+    // Supernodes and their steps.  Column c and its parent p (the first row of c) are merged when the pattern of c is
+    // {p} + pattern(p) -- equal counts suffice, pattern(c) \ {p} is always contained in pattern(p).  A supernode
+    // starts when every update from outside to any of its columns has been applied: step(S) = 1 + max step over the
+    // supernodes with an entry in a row of S.  Processing the supernodes by their LAST column is a topological
+    // order (an outside updater of c_j lies, with its whole chain, strictly below c_j in the elimination tree).
+    // Overwrites level[] with the step of the column's supernode.
+    void supernodes() {
+        auto cnt = [&](int c) { return Lp[c + 1] - Lp[c]; };
+        std::fill(snid.begin(), snid.end(), -1);
+        std::vector<std::vector<int>> mem;
+        for (int c = 0; c < N; ++c) {
+            if (snid[c] >= 0) continue;
+            const int id = (int)mem.size();
+            mem.emplace_back();
+            int cur = c;
+            snid[c] = id;
+            mem[id].push_back(c);
+            while ((int)mem[id].size() < sn_width && cnt(cur) > 0) {
+                const int p = Li[Lp[cur]];
+                if (cnt(p) + 1 != cnt(cur) || snid[p] >= 0) break;
+                snid[p] = id;
+                mem[id].push_back(p);
+                cur = p;
+            }
+        }
+        const int nsn = (int)mem.size();
+        std::vector<int> ord(nsn), step(nsn, 0);
+        for (int i = 0; i < nsn; ++i) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](int a, int b) { return mem[a].back() < mem[b].back(); });
+        for (int o = 0; o < nsn; ++o) {
+            const int sid = ord[o];
+            for (int c : mem[sid])
+                for (int p = Lp[c]; p < Lp[c + 1]; ++p) {
+                    const int r = snid[Li[p]];
+                    if (r != sid) step[r] = std::max(step[r], step[sid] + 1);
+                }
+        }
+        int nsteps = 0;
+        for (int c = 0; c < N; ++c) {
+            level[c] = step[snid[c]];
+            nsteps = std::max(nsteps, level[c] + 1);
+        }
+        // panels of the supernodes with more than one column, by step
+        pstep.assign(nsteps + 1, 0);
+        ptstep.assign(nsteps + 1, 0);
+        for (int sid = 0; sid < nsn; ++sid)
+            if (mem[sid].size() > 1) ++pstep[step[sid] + 1];
+        for (int l = 0; l < nsteps; ++l) pstep[l + 1] += pstep[l];
+        panels.resize(pstep[nsteps]);
+        std::vector<int> pos(pstep.begin(), pstep.end() - 1);
+        for (int wide = 1; wide >= 0; --wide)   // the wide panels of a step first
+            for (int sid = 0; sid < nsn; ++sid) {
+                if (mem[sid].size() < 2 || ((int)mem[sid].size() > kSnSmall) != (wide == 1)) continue;
+                KktPanel P = {};
+                P.w = (int)mem[sid].size();
+                P.nr = cnt(mem[sid].back());
+                for (int i = 0; i < P.w; ++i) {
+                    P.col[i] = mem[sid][i];
+                    P.node[i] = perm[mem[sid][i]];
+                    P.lp[i] = Lp[mem[sid][i]];
+                }
+                panels[pos[step[sid]]++] = P;
+            }
+        ptasks.clear();
+        ptwide.assign(nsteps, 0);
+        pwide.assign(nsteps, 0);
+        panel_slots = 0;
+        for (int l = 0; l < nsteps; ++l) {
+            for (int q = pstep[l]; q < pstep[l + 1]; ++q) {
+                panels[q].off = (int)panel_slots;
+                panel_slots += panels[q].w * (panels[q].w + 1) / 2;
+                if (panels[q].w > kSnSmall) ++pwide[l];
+                // narrow panels: every task redoes the small diagonal block, the first one stores it (a panel without
+                // rows still needs that); wide panels: the block is factorised by k_sn_diag, tasks are rows only
+                const bool wide = panels[q].w > kSnSmall;
+                const int rows = wide ? kPanelRowsWide : kPanelRows;
+                for (int r0 = 0; r0 < std::max(panels[q].nr, wide ? 0 : 1); r0 += rows) {
+                    ptasks.push_back(KktPanelTask{q, r0});
+                    if (wide) ++ptwide[l];
+                }
+            }
+            ptstep[l + 1] = (int)ptasks.size();
+        }
     }
 
     // chunk = maximal run of items with the same (step, target).  Reorders the items of every step (singles first) and
@@ -392,6 +548,30 @@ struct KktSymbolic {
             }
         };
         for (int l = 0; l < n_levels; ++l) {
+            for (int q = pstep[l]; q < pstep[l + 1]; ++q) {   // k_sn_factor: diagonal block (right-looking), then the rows
+                const KktPanel &P = panels[q];
+                const int w = P.w;
+                auto S = [&](int j, int i) -> double & { return W[P.lp[i] + j - i - 1]; };
+                for (int i = 0; i < w; ++i) {
+                    const double iv = 1.0 / diag[P.col[i]];
+                    invd[P.col[i]] = iv;
+                    for (int k = i + 1; k < w; ++k) {
+                        const double f = S(k, i) * iv;
+                        diag[P.col[k]] -= S(k, i) * f;
+                        for (int j = k + 1; j < w; ++j) S(j, k) -= S(j, i) * f;
+                    }
+                }
+                for (int t = 0; t < P.nr; ++t) {
+                    double y[kSnMax];
+                    for (int i = 0; i < w; ++i) {
+                        double &e = W[P.lp[i] + w - 1 - i + t];
+                        double acc = e;
+                        for (int k = 0; k < i; ++k) acc -= y[k] * S(i, k);
+                        e = acc;
+                        y[i] = acc * invd[P.col[i]];
+                    }
+                }
+            }
             for (int q = fs_beg[l]; q < fs_end[l]; ++q) apply(q, q + 1);
             for (int c = fmstep[l]; c < fmstep[l + 1]; ++c) apply(fmchunk[c].begin, fmchunk[c].end);
         }
@@ -403,13 +583,36 @@ struct KktSymbolic {
             for (int q = q0; q < q1; ++q) acc += W[fwd[q].pos] * v[fwd[q].src] * invd[fwd[q].k];
             v[fwd[q0].dst] -= acc;
         };
+        auto applyb = [&](int q0, int q1) {
+            double acc = 0.0;
+            for (int q = q0; q < q1; ++q) acc += invd[bwd[q].k] * W[bwd[q].pos] * v[bwd[q].src];
+            v[bwd[q0].dst] -= acc;
+        };
         for (int l = 0; l < n_levels; ++l) {
+            for (int q = pstep[l]; q < pstep[l + 1]; ++q) {   // k_sn_solve<true>
+                const KktPanel &P = panels[q];
+                for (int j = 1; j < P.w; ++j) {
+                    double acc = v[perm[P.col[j]]];
+                    for (int i = 0; i < j; ++i) acc -= W[P.lp[i] + j - i - 1] * invd[P.col[i]] * v[perm[P.col[i]]];
+                    v[perm[P.col[j]]] = acc;
+                }
+            }
             for (int q = ws_beg[l]; q < ws_end[l]; ++q) apply(q, q + 1);
             for (int c = wmstep[l]; c < wmstep[l + 1]; ++c) apply(wmchunk[c].begin, wmchunk[c].end);
         }
         for (int k = 0; k < N; ++k) v[perm[k]] *= invd[k];
-        for (int l = n_levels - 1; l >= 0; --l)
-            for (int q = bstep[l]; q < bstep[l + 1]; ++q) v[bwd[q].dst] -= invd[bwd[q].k] * W[bwd[q].pos] * v[bwd[q].src];
+        for (int l = n_levels - 1; l >= 0; --l) {
+            for (int q = pstep[l]; q < pstep[l + 1]; ++q) {   // k_sn_solve<false>
+                const KktPanel &P = panels[q];
+                for (int i = P.w - 2; i >= 0; --i) {
+                    double acc = v[perm[P.col[i]]];
+                    for (int j = i + 1; j < P.w; ++j) acc -= W[P.lp[i] + j - i - 1] * invd[P.col[i]] * v[perm[P.col[j]]];
+                    v[perm[P.col[i]]] = acc;
+                }
+            }
+            for (int q = bs_beg[l]; q < bs_end[l]; ++q) applyb(q, q + 1);
+            for (int c = bmstep[l]; c < bmstep[l + 1]; ++c) applyb(bmchunk[c].begin, bmchunk[c].end);
+        }
     }
 };
 

@@ -98,3 +98,47 @@ def test_toy_pattern(built_lib):
         corr, _ = _selftest(built_lib, J, dx, ew, rhs - M @ sol)
         sol = sol + corr
     assert np.allclose(sol, ref, rtol=1e-10)
+
+
+@pytest.mark.parametrize("width", ["1", "4", "16"])
+def test_supernodes_dense_block(built_lib, monkeypatch, width):
+    """A dense K makes the whole elimination tree one chain: with supernodes it is cut into panels of at most `width`
+    columns (diagonal block + rows below, k_sn_factor / k_sn_solve on the device), each updating the next through the
+    chunked term lists.  Same answer as without (width 1) and as scipy."""
+    monkeypatch.setenv("ASM_IPM_SUPERNODE", width)
+    rng = np.random.default_rng(11)
+    m, n = 23, 31
+    K = sp.csr_matrix(rng.standard_normal((m, n)))
+    dx = 10.0 ** rng.uniform(-3, 3, n)
+    ew = 10.0 ** rng.uniform(-3, 3, m)
+    rhs = rng.standard_normal(n + m)
+    sol, st = _selftest(built_lib, K, dx, ew, rhs)
+    ref = spla.spsolve(_kkt(K, dx, ew), rhs)
+    assert np.linalg.norm(sol - ref) <= 1e-9 * np.linalg.norm(ref)
+    # the n column nodes are independent (level 0); the first of them and the m row nodes form one chain of m + 1
+    # columns with nested patterns: a level each without supernodes, ceil((m + 1) / width) steps with them
+    chain = m + 1
+    assert st["levels"] == {"1": chain, "4": 1 + -(-chain // 4), "16": 1 + -(-chain // 16)}[width]
+
+
+def test_supernodes_shorten_the_schedule(built_lib, monkeypatch):
+    """case118-sized ACOPF KKT: the supernodal schedule has several times fewer steps and target updates, and the host
+    mirror of the device numerics gives the same solution."""
+    mdl = acopf.AcopfModel(acopf.synthetic_network(*acopf.PEGASE_SHAPES["case118"]))
+    x = np.clip(mdl.x0, mdl.x_L, mdl.x_U)
+    dE = mdl.eval_jac_g(x, "eval", None, None, np.zeros(mdl.nnz))
+    J = sp.coo_matrix((dE, (mdl.j_str[:, 0] - 1, mdl.j_str[:, 1] - 1)), shape=(mdl.m, mdl.n)).tocsr()
+    J.sum_duplicates()
+    rng = np.random.default_rng(7)
+    dx = 10.0 ** rng.uniform(-2, 2, mdl.n)
+    ew = 10.0 ** rng.uniform(-2, 2, mdl.m)
+    rhs = rng.standard_normal(mdl.n + mdl.m)
+    out = {}
+    for width in ("1", "16"):
+        monkeypatch.setenv("ASM_IPM_SUPERNODE", width)
+        out[width] = _selftest(built_lib, J, dx, ew, rhs)
+    (s1, st1), (s16, st16) = out["1"], out["16"]
+    assert np.linalg.norm(s1 - s16) <= 1e-10 * np.linalg.norm(s1)
+    assert st16["levels"] * 2 < st1["levels"]
+    assert st16["chunks"] * 2 < st1["chunks"]
+    assert st16["nnz_L"] == st1["nnz_L"]
