@@ -215,7 +215,9 @@ def kkt_bytes(st, B):
     nothing survives in L2 from one level to the next when the batch working set (nnz(L) * B * 8 bytes) is much larger
     than L2.  Index lists are read once per warp, i.e. once per 32 scenarios.  Operands that several chunks of one
     level share are counted once -- the kernel re-reads them (from L1 / L2), so this is a lower bound of what it moves
-    and `achieved` is conservative."""
+    and `achieved` is conservative.  With supernodes a "level" is a step of the supernodal schedule and the panels are
+    in the same two counters (every panel entry read and written once, the factorised diagonal block read once per row
+    task): the symbolic analysis adds them, csrc/kkt_symbolic.hpp."""
     fr, ft = st["factor_distinct_reads"], st["factor_targets"]
     sr, stg = st["substitution_distinct_reads"], st["substitution_targets"]
     nnzL, N, terms = st["nnz_L"], st["kkt_dim"], st["terms"]
@@ -420,15 +422,17 @@ def run_ours(a):
         newton = its_sum / total_scen
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(f"k_ldl_factor:{a.case}:{S}")
+                sched = "levels" if os.environ.get("ASM_IPM_SUPERNODE") == "1" else "supernodal"
+                traffic = json.load(open(tpath)).get(f"ldl_factor:{sched}:{a.case}:{S}")
             except (OSError, ValueError):
                 traffic = None
         achieved = by_fac / (fac_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic,
                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
-                    "kernel": "k_ldl_factor: one numeric L D L' of the KKT matrices of the whole batch (one launch per "
-                              "level of the elimination tree, replayed as a CUDA graph)",
+                    "kernel": "one numeric L D L' of the KKT matrices of the whole batch, replayed as one CUDA graph: per step "
+                              "of the supernodal schedule k_sn_diag + k_sn_rows (dense panels of the supernodes) and "
+                              "k_ldl_factor (chunked updates that leave them)",
                     "bytes_per_launch": by_fac, "factor_ms": fac_ms, "launches_per_factorisation": kst["launches_factor"],
                     "substitution_pair_ms": pair_ms, "substitution_pair_bytes": by_pair,
                     "substitution_pair_gbs": by_pair / (pair_ms * 1e-3) / 1e9,
