@@ -248,19 +248,24 @@ int asm_slp_last_solve_timing(asm_slp *h, double *loop_ms, int64_t *iterations);
  * whether the matrix values stay resident there, and the padded entry count of the row side */
 int asm_plan_check(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, int32_t G,
                    int64_t *smem_bytes, int32_t *matrix_resident, int64_t *padded_entries);
-/* barrier engine (engine 0 / 4) instrumentation.  stats[14]: KKT dimension, nnz(L), update terms, levels, factor chunks,
+/* barrier engine (engine 0 / 4) instrumentation.  stats[14]: KKT dimension, nnz(L), update terms outside the supernode
+ * panels, steps of the schedule (levels of the elimination tree when supernodes are off), factor chunks,
  * forward-substitution chunks, kernel launches per factorisation, per substitution pair, factorisations and substitution
  * pairs of the last solve, distinct f64 operands read / targets updated per factorisation and per substitution pair
  * (summed over the levels: the compulsory HBM traffic of a batch larger than L2); times[4]: symbolic analysis
- * ms, Newton steps of the last solve, factor / solve ms of the traced step (ASM_TRACE=1).  Either pointer may be NULL */
+ * ms, Newton steps of the last solve, factor / solve ms of the traced step (ASM_TRACE=1).  Either pointer may be NULL.
+ * Environment switches read when a handle builds its engine: ASM_IPM_SUPERNODE / ASM_IPM_SUPERNODE_SINGLE = widest
+ * supernode for batches / single LPs (default 16, 1 = one column per level), ASM_IPM_NARROW = items below which runs of
+ * levels are fused into one block (level schedule only), ASM_NO_PDL = plain stream-ordered launches */
 int asm_slp_ipm_info(asm_slp *h, int64_t *stats, double *times);
 /* average device time (CUDA events on the handle's stream) of one numeric factorisation and one substitution pair of
  * the whole batch, `reps` launches each, on the data of the last solve */
 int asm_slp_ipm_timing(asm_slp *h, int32_t reps, double *factor_ms, double *solve_ms);
 /* host-only self test of the barrier engine's symbolic analysis (no device needed): factorises
  * [-diag(dx) K'; K diag(ew)] and solves one right-hand side on the host with the lists and the summation order of the
- * device kernels.  rhs_sol[n_cols + n_rows]: right-hand side in, solution out.  stats[8]: nnz(L), terms, levels,
- * factor / forward / backward launches, longest chunk, chunks */
+ * device kernels (supernodes as a batch handle would use them).  rhs_sol[n_cols + n_rows]: right-hand side in,
+ * solution out.  stats[8]: nnz(L), terms, steps, factor / forward / backward launches of the level plan, longest chunk,
+ * chunks */
 int asm_kkt_selftest(int32_t n_cols, int32_t n_rows, const int64_t *row_ptr, const int32_t *col_idx, const double *vals,
                      const double *dx, const double *ew, double *rhs_sol, int64_t *stats);
 
