@@ -142,3 +142,33 @@ def test_supernodes_shorten_the_schedule(built_lib, monkeypatch):
     assert st16["levels"] * 2 < st1["levels"]
     assert st16["chunks"] * 2 < st1["chunks"]
     assert st16["nnz_L"] == st1["nnz_L"]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_supernodes_random_structures(built_lib, monkeypatch, seed):
+    """Patterns that produce supernodes of every width, wide panels with and without rows below them, chains longer
+    than one supernode and columns with several rows in one supernode (chunks in the backward substitution): block
+    diagonal dense blocks coupled by a few dense rows, plus random sparse noise.  Every width gives scipy's answer."""
+    rng = np.random.default_rng(100 + seed)
+    blocks = [sp.csr_matrix(rng.standard_normal((int(rng.integers(2, 9)), int(rng.integers(2, 12)))))
+              for _ in range(int(rng.integers(2, 6)))]
+    K = sp.block_diag(blocks, format="csr")
+    m0, n = K.shape
+    coupling = sp.random(int(rng.integers(1, 5)), n, density=0.6, random_state=seed, format="csr")
+    noise = sp.random(m0, n, density=0.02, random_state=seed + 50, format="csr")
+    K = sp.vstack([K + noise, coupling], format="csr")
+    K.data[:] = rng.standard_normal(K.nnz)
+    m = K.shape[0]
+    dx = 10.0 ** rng.uniform(-4, 2, n)
+    ew = 10.0 ** rng.uniform(-4, 2, m)
+    ew[rng.random(m) < 0.3] = 1e-8            # equality rows: only the regularisation on the diagonal
+    rhs = rng.standard_normal(n + m)
+    ref = spla.spsolve(_kkt(K, dx, ew), rhs)
+    levels = {}
+    for width in ("1", "2", "5", "16"):
+        monkeypatch.setenv("ASM_IPM_SUPERNODE", width)
+        sol, st = _selftest(built_lib, K, dx, ew, rhs)
+        assert np.linalg.norm(sol - ref) <= 1e-7 * np.linalg.norm(ref), width
+        levels[width] = st["levels"]
+    # a supernode never starts later than the level of its last column: steps <= levels for every width
+    assert max(levels["2"], levels["5"], levels["16"]) <= levels["1"]
