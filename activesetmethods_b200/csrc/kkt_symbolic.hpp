@@ -33,11 +33,27 @@
 // No CUDA in this header: it is also compiled into the host-only self test (asm_kkt_selftest).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <algorithm>
+#include <atomic>
 #include <functional>
+#include <thread>
 #include <queue>
 #include <utility>
 #include <vector>
+
+#ifdef KKT_PROFILE
+#include <chrono>
+#include <cstdio>
+#define KKT_PHASE(name)                                                                                           \
+    do {                                                                                                          \
+        const auto now__ = std::chrono::steady_clock::now();                                                      \
+        fprintf(stderr, "[kkt] %-28s %8.3f s\n", name, std::chrono::duration<double>(now__ - t_phase__).count()); \
+        t_phase__ = now__;                                                                                        \
+    } while (0)
+#else
+#define KKT_PHASE(name) ((void)0)
+#endif
 
 namespace asmb {
 
@@ -73,6 +89,38 @@ struct KktPanel {                  // a supernode of 2..kSnMax columns c_0 < c_1
 struct KktPanelTask {
     int panel, r0;                 // rows [r0, r0 + kPanelRows(Wide)) of the panel
 };
+
+// f(i) for every i in [0, n) on the host's cores, in dynamically claimed chunks.  Everything built with it writes to
+// positions that are fixed beforehand, so the result does not depend on the number of threads (ASM_HOST_THREADS caps it)
+template <class F>
+inline void kkt_parallel_for(int n, int chunk, F f) {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (const char *e = getenv("ASM_HOST_THREADS")) nt = (unsigned)atoi(e);
+    nt = std::max(1u, std::min(nt, 16u));
+    if (nt == 1 || n <= chunk) {
+        for (int i = 0; i < n; ++i) f(i);
+        return;
+    }
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            const int b = next.fetch_add(chunk);
+            if (b >= n) break;
+            const int e = std::min(n, b + chunk);
+            for (int i = b; i < e; ++i) f(i);
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) {
+        try {
+            th.emplace_back(worker);
+        } catch (...) {   // no more threads to be had: the ones we have (at least this one) do the work
+            break;
+        }
+    }
+    worker();
+    for (std::thread &x : th) x.join();
+}
 
 struct KktSymbolic {
     int n = 0, m = 0, N = 0;
@@ -122,6 +170,9 @@ struct KktSymbolic {
         n = n_;
         m = m_;
         N = n + m;
+#ifdef KKT_PROFILE
+        auto t_phase__ = std::chrono::steady_clock::now();
+#endif
         std::vector<std::vector<int>> adj(N);
         for (int i = 0; i < m; ++i)
             for (int q = row_ptr[i]; q < row_ptr[i + 1]; ++q) {
@@ -182,6 +233,7 @@ struct KktSymbolic {
         }
         adj.clear();
         adj.shrink_to_fit();
+        KKT_PHASE("minimum degree");
         // ---- pattern of L in the permuted numbering
         Lp.assign(N + 1, 0);
         for (int k = 0; k < N; ++k) Lp[k + 1] = Lp[k] + (int)colpat[perm[k]].size();
@@ -217,6 +269,7 @@ struct KktSymbolic {
         if (sn_width > 1) supernodes();
         n_levels = 0;
         for (int k = 0; k < N; ++k) n_levels = std::max(n_levels, level[k] + 1);
+        KKT_PHASE("pattern, levels, supernodes");
         if (panels.empty()) {
             pstep.assign(n_levels + 1, 0);
             ptstep.assign(n_levels + 1, 0);
@@ -227,49 +280,90 @@ struct KktSymbolic {
         // ---- terms, target-major first (column k updates entry (r_a, r_b) and pivot r_b for every pair of its rows
         //      r_a >= r_b), then a stable counting sort by the level of k: (level, target, k) order
         const int64_t n_targets = nnzL + N;
+        // rows of L: (column k, position of the entry) of row j, k ascending
+        std::vector<int> rptr(N + 1, 0), rcol(nnzL), rpos(nnzL);
         {
-            std::vector<int64_t> cnt(n_targets + 1, 0);
-            std::vector<KktTerm> tm;
-            for (int pass = 0; pass < 2; ++pass) {
-                for (int k = 0; k < N; ++k) {
-                    const int p0 = Lp[k], p1 = Lp[k + 1];
-                    for (int pb = p0; pb < p1; ++pb) {
-                        const int j = Li[pb];
-                        if (snid[j] == snid[k]) {   // target column in the supernode of k: the panel kernel's work
-                            if (pass == 0) n_intra += p1 - pb;
-                            continue;
-                        }
-                        const int64_t td = nnzL + j;
-                        if (pass == 0)
-                            ++cnt[td + 1];
-                        else
-                            tm[cnt[td]++] = KktTerm{pb, pb, k, (int)td};
-                        int ptr = Lp[j];
-                        for (int pa = pb + 1; pa < p1; ++pa) {
-                            const int i = Li[pa];
-                            while (Li[ptr] < i) ++ptr;  // (i, j) exists: fill of column k
-                            if (pass == 0)
-                                ++cnt[(int64_t)ptr + 1];
-                            else
-                                tm[cnt[ptr]++] = KktTerm{pa, pb, k, ptr};
-                        }
+            for (int64_t p = 0; p < nnzL; ++p) ++rptr[Li[p] + 1];
+            for (int k = 0; k < N; ++k) rptr[k + 1] += rptr[k];
+            std::vector<int> pos(rptr.begin(), rptr.end() - 1);
+            for (int k = 0; k < N; ++k)
+                for (int p = Lp[k]; p < Lp[k + 1]; ++p) {
+                    rcol[pos[Li[p]]] = k;
+                    rpos[pos[Li[p]]++] = p;
+                }
+        }
+        {
+            // The targets in column j (its entries and its pivot) get their terms from the columns k of row j: entry
+            // (j, k) at position pb pairs with every entry (i, k) below it.  Sizes are known without searching (one
+            // term per such pair), so every column writes its own slice of the target-major list, in parallel.
+            std::vector<int64_t> eoff(N + 1, 0), poff(N + 1, 0);
+            for (int j = 0; j < N; ++j) {
+                int64_t ce = 0, cp = 0;
+                for (int q = rptr[j]; q < rptr[j + 1]; ++q) {
+                    const int k = rcol[q];
+                    if (snid[j] == snid[k]) {   // target column in the supernode of k: the panel kernel's work
+                        n_intra += Lp[k + 1] - rpos[q];
+                        continue;
+                    }
+                    ce += Lp[k + 1] - rpos[q] - 1;
+                    ++cp;
+                }
+                eoff[j + 1] = eoff[j] + ce;
+                poff[j + 1] = poff[j] + cp;
+            }
+            nterms = eoff[N] + poff[N];
+            if (nterms > 0x3fffffffLL || n_targets >= kLastBit) return -1;
+            std::vector<KktTerm> tm(nterms);
+            const int64_t pbase = eoff[N];
+            kkt_parallel_for(N, 64, [&](int jj) {
+                const int j = N - 1 - jj;   // the heavy columns (root of the tree) first
+                static thread_local std::vector<KktTerm> tmp;
+                static thread_local std::vector<int> cnt;
+                const int c0 = Lp[j], nc = Lp[j + 1] - Lp[j];
+                tmp.clear();
+                cnt.assign(nc + 1, 0);
+                int64_t pp = pbase + poff[j];
+                for (int q = rptr[j]; q < rptr[j + 1]; ++q) {
+                    const int k = rcol[q], pb = rpos[q];
+                    if (snid[j] == snid[k]) continue;
+                    tm[pp++] = KktTerm{pb, pb, k, (int)(nnzL + j)};
+                    int ptr = c0;
+                    for (int pa = pb + 1; pa < Lp[k + 1]; ++pa) {
+                        const int i = Li[pa];
+                        while (Li[ptr] < i) ++ptr;   // (i, j) exists: fill of column k
+                        tmp.push_back(KktTerm{pa, pb, k, ptr});
+                        ++cnt[ptr - c0 + 1];
                     }
                 }
-                if (pass == 0) {
-                    for (int64_t t = 0; t < n_targets; ++t) cnt[t + 1] += cnt[t];
-                    nterms = cnt[n_targets];
-                    if (nterms > 0x3fffffffLL || n_targets >= kLastBit) return -1;
-                    tm.resize(nterms);  // cnt[t] is now the running write position of target t
+                for (int t = 0; t < nc; ++t) cnt[t + 1] += cnt[t];
+                KktTerm *out = tm.data() + eoff[j];
+                for (const KktTerm &u : tmp) out[cnt[u.t - c0]++] = u;   // stable: (target, k) order
+            });
+            // stable counting sort by the level of k with per-slice histograms: (level, target, k) order
+            const int nsl = 64;
+            std::vector<int64_t> hist((size_t)nsl * n_levels, 0);
+            auto slice = [&](int t) { return nterms * t / nsl; };
+            kkt_parallel_for(nsl, 1, [&](int t) {
+                int64_t *h = hist.data() + (size_t)t * n_levels;
+                for (int64_t q = slice(t); q < slice(t + 1); ++q) ++h[level[tm[q].k]];
+            });
+            int64_t run = 0;
+            for (int l = 0; l < n_levels; ++l)
+                for (int t = 0; t < nsl; ++t) {
+                    const int64_t c = hist[(size_t)t * n_levels + l];
+                    hist[(size_t)t * n_levels + l] = run;
+                    run += c;
                 }
-            }
-            std::vector<int64_t> lpos(n_levels + 1, 0);
-            for (const KktTerm &u : tm) ++lpos[level[u.k] + 1];
-            for (int l = 0; l < n_levels; ++l) lpos[l + 1] += lpos[l];
             terms.resize(nterms);
-            for (const KktTerm &u : tm) terms[lpos[level[u.k]]++] = u;
+            kkt_parallel_for(nsl, 1, [&](int t) {
+                int64_t *h = hist.data() + (size_t)t * n_levels;
+                for (int64_t q = slice(t); q < slice(t + 1); ++q) terms[h[level[tm[q].k]]++] = tm[q];
+            });
         }
+        KKT_PHASE("terms");
         n_fchunks = regroup(terms, [&](const KktTerm &u) { return level[u.k]; }, [](const KktTerm &u) { return u.t; },
                             fs_beg, fs_end, fmstep, fmchunk);
+        KKT_PHASE("regroup terms");
         {   // the last chunk of every pivot inverts it
             std::vector<int> last(N, -1);
             for (size_t q = 0; q < terms.size(); ++q)
@@ -286,13 +380,9 @@ struct KktSymbolic {
         }
         // ---- forward substitution: row-major items (target i, sources ascending), then by level of the source
         {
-            std::vector<int> rptr(N + 1, 0);
-            for (int64_t p = 0; p < nnzL; ++p) ++rptr[Li[p] + 1];
-            for (int k = 0; k < N; ++k) rptr[k + 1] += rptr[k];
             std::vector<KktFwdItem> rl(nnzL);
-            std::vector<int> pos(rptr.begin(), rptr.end() - 1);
-            for (int k = 0; k < N; ++k)
-                for (int p = Lp[k]; p < Lp[k + 1]; ++p) rl[pos[Li[p]]++] = KktFwdItem{p, perm[k], k, perm[Li[p]]};
+            for (int j = 0; j < N; ++j)
+                for (int q = rptr[j]; q < rptr[j + 1]; ++q) rl[q] = KktFwdItem{rpos[q], perm[rcol[q]], rcol[q], perm[j]};
             std::vector<int64_t> lpos(n_levels + 1, 0);
             int64_t kept = 0;
             for (const KktFwdItem &u : rl)
@@ -319,6 +409,7 @@ struct KktSymbolic {
         }
         regroup(bwd, [&](const KktBwdItem &u) { return level[inv[u.src]]; }, [](const KktBwdItem &u) { return u.dst; },
                 bs_beg, bs_end, bmstep, bmchunk);
+        KKT_PHASE("substitution lists");
         auto work = [&](const std::vector<int> &sb, const std::vector<int> &se, const std::vector<int> &ms) {
             std::vector<int> w(n_levels + 1, 0);
             for (int l = 0; l < n_levels; ++l) w[l + 1] = w[l] + (se[l] - sb[l]) + (ms[l + 1] - ms[l]);
@@ -370,6 +461,7 @@ struct KktSymbolic {
                 b_targets += P.w;
             }
         }
+        KKT_PHASE("traffic statistics");
         plan(work(fs_beg, fs_end, fmstep), narrow, flaunch);
         plan(work(ws_beg, ws_end, wmstep), narrow, wlaunch);
         plan(work(bs_beg, bs_end, bmstep), narrow, blaunch);
@@ -470,35 +562,52 @@ struct KktSymbolic {
         send.assign(n_levels, 0);
         mstep.assign(n_levels + 1, 0);
         mchunk.clear();
-        std::vector<T> out;
-        out.reserve(items.size());
-        int64_t n_chunks = 0;
-        size_t q = 0;
-        for (int l = 0; l < n_levels; ++l) {
-            const size_t q0 = q;
-            while (q < items.size() && lvl(items[q]) == l) ++q;
-            sbeg[l] = (int)out.size();
+        // the items of a step stay in the step's range: the steps are independent of each other
+        std::vector<size_t> lo(n_levels + 1, 0);
+        {
+            size_t q = 0;
+            for (int l = 0; l < n_levels; ++l) {
+                lo[l] = q;
+                while (q < items.size() && lvl(items[q]) == l) ++q;
+            }
+            lo[n_levels] = q;
+        }
+        std::vector<T> out(items.size());
+        std::vector<std::vector<KktRange>> mc(n_levels);
+        std::vector<int64_t> nch(n_levels, 0);
+        std::vector<int> longest(n_levels, 0);
+        kkt_parallel_for(n_levels, 1, [&](int l) {
+            const size_t q0 = lo[l], q = lo[l + 1];
+            size_t w = q0;
             // pass 1: singles
             for (size_t a = q0; a < q;) {
                 size_t b = a + 1;
                 while (b < q && tgt(items[b]) == tgt(items[a])) ++b;
-                if (b - a == 1) out.push_back(items[a]);
+                if (b - a == 1) out[w++] = items[a];
                 a = b;
             }
-            send[l] = (int)out.size();
+            sbeg[l] = (int)q0;
+            send[l] = (int)w;
             // pass 2: multi-item chunks
             for (size_t a = q0; a < q;) {
                 size_t b = a + 1;
                 while (b < q && tgt(items[b]) == tgt(items[a])) ++b;
-                ++n_chunks;
+                ++nch[l];
                 if (b - a > 1) {
-                    mchunk.push_back(KktRange{(int)out.size(), (int)(out.size() + (b - a))});
-                    out.insert(out.end(), items.begin() + a, items.begin() + b);
-                    longest_chunk = std::max(longest_chunk, (int)(b - a));
+                    mc[l].push_back(KktRange{(int)w, (int)(w + (b - a))});
+                    std::copy(items.begin() + a, items.begin() + b, out.begin() + w);
+                    w += b - a;
+                    longest[l] = std::max(longest[l], (int)(b - a));
                 }
                 a = b;
             }
+        });
+        int64_t n_chunks = 0;
+        for (int l = 0; l < n_levels; ++l) {
+            mchunk.insert(mchunk.end(), mc[l].begin(), mc[l].end());
             mstep[l + 1] = (int)mchunk.size();
+            n_chunks += nch[l];
+            longest_chunk = std::max(longest_chunk, longest[l]);
         }
         items.swap(out);
         return n_chunks;

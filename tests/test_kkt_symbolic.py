@@ -172,3 +172,24 @@ def test_supernodes_random_structures(built_lib, monkeypatch, seed):
         levels[width] = st["levels"]
     # a supernode never starts later than the level of its last column: steps <= levels for every width
     assert max(levels["2"], levels["5"], levels["16"]) <= levels["1"]
+
+
+def test_host_threads_do_not_change_the_lists(built_lib, monkeypatch):
+    """The symbolic analysis builds its lists on several host threads; every thread writes to positions fixed
+    beforehand, so the numeric result is bit-identical for any thread count."""
+    mdl = acopf.AcopfModel(acopf.synthetic_network(*acopf.PEGASE_SHAPES["case118"]))
+    x = np.clip(mdl.x0, mdl.x_L, mdl.x_U)
+    dE = mdl.eval_jac_g(x, "eval", None, None, np.zeros(mdl.nnz))
+    J = sp.coo_matrix((dE, (mdl.j_str[:, 0] - 1, mdl.j_str[:, 1] - 1)), shape=(mdl.m, mdl.n)).tocsr()
+    J.sum_duplicates()
+    rng = np.random.default_rng(3)
+    dx = 10.0 ** rng.uniform(-6, 2, mdl.n)
+    ew = 10.0 ** rng.uniform(-6, 2, mdl.m)
+    rhs = rng.standard_normal(mdl.n + mdl.m)
+    out = []
+    for threads in ("1", "2", "7"):
+        monkeypatch.setenv("ASM_HOST_THREADS", threads)
+        out.append(_selftest(built_lib, J, dx, ew, rhs))
+    for sol, st in out[1:]:
+        assert np.array_equal(sol, out[0][0])
+        assert st == out[0][1]
