@@ -6,14 +6,14 @@
 // linearised power-flow equations are an ill-conditioned, almost square equality system; a barrier method needs
 // 20 - 40 Newton steps, and every Newton step of every LP of a batch and of every SLP iteration factorises a matrix
 // with the SAME sparsity pattern (the Jacobian pattern is uploaded once, src/model.jl:10).  So:
-//   * symbolic work once per handle on the host (kkt_symbolic.hpp): ordering, pattern of L, level schedule, the
-//     fan-out lists of update products grouped by the level of their source column;
-//   * numeric L D L' of the quasi-definite system  [-(Dx + d) K'; K (Ew + d)]  on the device, one launch per level
-//     (k_ldl_factor), every target written by exactly one thread per level, scenarios across the lanes of a warp
-//     (element-major v[i * B + s]: index loads are warp-uniform, value loads coalesced); no pivoting, no atomics,
-//     bit-reproducible;
-//   * level-scheduled substitutions (k_ldl_fwd / k_ldl_diag / k_ldl_bwd), iterative refinement against the
-//     unregularised matrix on demand (k_kkt_res_*); the level kernels are programmatic dependents of one another
+//   * symbolic work once per handle on the host (kkt_symbolic.hpp): ordering, pattern of L, supernodes, step schedule,
+//     the fan-out lists of update products grouped by the step of their source column;
+//   * numeric L D L' of the quasi-definite system  [-(Dx + d) K'; K (Ew + d)]  on the device: per step the dense panels
+//     of its supernodes (k_sn_diag, k_sn_rows), then the updates that leave them (k_ldl_factor), every target written
+//     by exactly one thread per step, scenarios across the lanes of a warp (element-major v[i * B + s]: index loads are
+//     warp-uniform, value loads coalesced); no pivoting, no atomics, bit-reproducible;
+//   * step-scheduled substitutions (k_sn_solve, k_ldl_fwd / k_ldl_diag / k_ldl_bwd), iterative refinement against the
+//     unregularised matrix on demand (k_kkt_res_*); the step kernels are programmatic dependents of one another
 //     and the three launch sequences are captured once as CUDA graphs;
 //   * Mehrotra predictor-corrector with every scalar decision taken on the device per scenario (k_ipm_decide,
 //     k_ipm_scalars); the host enqueues a fixed kernel sequence per Newton step and reads two 4-byte counters.
