@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <atomic>
 #include <functional>
+#include <memory>
 #include <thread>
 #include <queue>
 #include <utility>
@@ -313,7 +314,8 @@ struct KktSymbolic {
             }
             nterms = eoff[N] + poff[N];
             if (nterms > 0x3fffffffLL || n_targets >= kLastBit) return -1;
-            std::vector<KktTerm> tm(nterms);
+            std::unique_ptr<KktTerm[]> tm_buf(new KktTerm[std::max<int64_t>(nterms, 1)]);   // no zero fill: every slot is written below
+            KktTerm *const tm = tm_buf.get();
             const int64_t pbase = eoff[N];
             kkt_parallel_for(N, 64, [&](int jj) {
                 const int j = N - 1 - jj;   // the heavy columns (root of the tree) first
@@ -336,7 +338,7 @@ struct KktSymbolic {
                     }
                 }
                 for (int t = 0; t < nc; ++t) cnt[t + 1] += cnt[t];
-                KktTerm *out = tm.data() + eoff[j];
+                KktTerm *out = tm + eoff[j];
                 for (const KktTerm &u : tmp) out[cnt[u.t - c0]++] = u;   // stable: (target, k) order
             });
             // stable counting sort by the level of k with per-slice histograms: (level, target, k) order
@@ -572,30 +574,32 @@ struct KktSymbolic {
             }
             lo[n_levels] = q;
         }
-        std::vector<T> out(items.size());
         std::vector<std::vector<KktRange>> mc(n_levels);
         std::vector<int64_t> nch(n_levels, 0);
         std::vector<int> longest(n_levels, 0);
         kkt_parallel_for(n_levels, 1, [&](int l) {
             const size_t q0 = lo[l], q = lo[l + 1];
+            static thread_local std::vector<T> in;   // the step's items in their old order; rewritten in place
+            in.assign(items.begin() + q0, items.begin() + q);
+            const size_t cnt = q - q0;
             size_t w = q0;
             // pass 1: singles
-            for (size_t a = q0; a < q;) {
+            for (size_t a = 0; a < cnt;) {
                 size_t b = a + 1;
-                while (b < q && tgt(items[b]) == tgt(items[a])) ++b;
-                if (b - a == 1) out[w++] = items[a];
+                while (b < cnt && tgt(in[b]) == tgt(in[a])) ++b;
+                if (b - a == 1) items[w++] = in[a];
                 a = b;
             }
             sbeg[l] = (int)q0;
             send[l] = (int)w;
             // pass 2: multi-item chunks
-            for (size_t a = q0; a < q;) {
+            for (size_t a = 0; a < cnt;) {
                 size_t b = a + 1;
-                while (b < q && tgt(items[b]) == tgt(items[a])) ++b;
+                while (b < cnt && tgt(in[b]) == tgt(in[a])) ++b;
                 ++nch[l];
                 if (b - a > 1) {
                     mc[l].push_back(KktRange{(int)w, (int)(w + (b - a))});
-                    std::copy(items.begin() + a, items.begin() + b, out.begin() + w);
+                    std::copy(in.begin() + a, in.begin() + b, items.begin() + w);
                     w += b - a;
                     longest[l] = std::max(longest[l], (int)(b - a));
                 }
@@ -609,7 +613,6 @@ struct KktSymbolic {
             n_chunks += nch[l];
             longest_chunk = std::max(longest_chunk, longest[l]);
         }
-        items.swap(out);
         return n_chunks;
     }
 
